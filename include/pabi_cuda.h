@@ -1,0 +1,138 @@
+/*
+ * pabi_cuda.h -- C ABI of libpabi_b200.so, the B200-native replacement for the
+ * perft / legal-move-generation path of kirillbobyrev/pabi.
+ *
+ * pabi has no FFI of its own (pure Rust); the boundary it would bind is its
+ * public `pabi::chess` API.  Each entry point below cites the Rust item it
+ * replaces (paths relative to the pabi crate root); INTEGRATION.md shows the
+ * `extern "C"` block and build.rs hook a maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; nothing is retained by the callee except
+ *    inside the opaque context;
+ *  - status codes: 0 ok; < 0 a parse / validation / argument error (message in
+ *    the caller's buffer or pabi_cuda_last_error); > 0 a CUDA error code
+ *    (cudaError_t).  There is NO CPU fallback: every move-generation, make-move
+ *    and perft entry point runs on the device or fails;
+ *  - one context owns one device; calls on one context must be serialised by
+ *    the caller, different contexts may be used concurrently.
+ */
+#ifndef PABI_CUDA_H
+#define PABI_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Image of `Position` (src/chess/position.rs:45-63) with `Pieces`
+ * (src/chess/bitboard.rs:350-357) inlined in field order; 112 bytes. */
+typedef struct {
+  uint64_t white[6];          /* king, queens, rooks, bishops, knights, pawns */
+  uint64_t black[6];
+  uint64_t hash;              /* carried through, never interpreted (Zobrist keys are build-random,
+                                 src/chess/generated.rs:15-16) */
+  uint16_t fullmove_counter;
+  uint8_t castling;           /* src/chess/core.rs:604-612: 1 K, 2 Q, 4 k, 8 q */
+  uint8_t side_to_move;       /* src/environment.rs:13-16: 0 white, 1 black */
+  uint8_t halfmove_clock;
+  uint8_t en_passant_square;  /* 0..63 (A1 = 0, H8 = 63, src/chess/core.rs:169-182), 64 = None */
+  uint8_t _pad[2];
+} pabi_position_t;
+
+/* `Move` (src/chess/core.rs:24-66): bits 0-5 from, 6-11 to, 12-14 promotion
+ * (0 none, 1 knight, 2 bishop, 3 rook, 4 queen; core.rs:700-705). */
+typedef uint16_t pabi_move_t;
+#define PABI_MAX_MOVES 256 /* MoveList = ArrayVec<Move, 256>, src/chess/core.rs:139-145 */
+
+typedef struct pabi_cuda_ctx pabi_cuda_ctx; /* device, stream, frontier buffers, staged tables */
+
+typedef struct {
+  double device_ms;           /* CUDA-event time on the context's stream, first launch to last */
+  double host_ms;             /* wall time of the call, copies included */
+  uint64_t algorithmic_bytes; /* 2 * 64 B * interior nodes (perft) or 64N + 4(N+1) + 2M (lists) */
+  uint64_t kernel_launches;   /* kernels launched by the call */
+  uint64_t interior_nodes;    /* positions for which moves were generated */
+  uint64_t reserved[3];
+} pabi_timing_t;
+
+/* ---- host-side text API (no device work) -------------------------------- */
+/* Position::starting(), src/chess/position.rs:78-91 */
+void pabi_position_starting(pabi_position_t* out);
+/* Position::from_fen(&str), src/chess/position.rs:157-275 (strict, then validate :934-1032) */
+int pabi_position_from_fen(const char* fen, pabi_position_t* out, char* err, size_t err_cap);
+/* impl TryFrom<&str> for Position, src/chess/position.rs:809-821 (trim, optional "fen "/"epd " prefix) */
+int pabi_position_parse(const char* text, pabi_position_t* out, char* err, size_t err_cap);
+/* impl Display for Position, src/chess/position.rs:823-860; returns the length, < 0 if cap is too small */
+int pabi_position_to_fen(const pabi_position_t* p, char* out, size_t cap);
+/* Move::from_uci / impl Display for Move, src/chess/core.rs:105-134 */
+int pabi_move_from_uci(const char* uci, pabi_move_t* out);
+int pabi_move_to_uci(pabi_move_t mv, char out[6]);
+
+/* ---- device path --------------------------------------------------------- */
+/* device < 0 selects the current CUDA device.  frontier_capacity = positions per
+ * breadth-first level buffer (0 = default). */
+int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out);
+void pabi_cuda_destroy(pabi_cuda_ctx* ctx);
+const char* pabi_cuda_last_error(pabi_cuda_ctx* ctx);
+int pabi_cuda_device(const pabi_cuda_ctx* ctx);
+
+/* perft(&Position, depth), src/chess/position.rs:909-924 */
+int pabi_cuda_perft(pabi_cuda_ctx* ctx, const pabi_position_t* root, uint8_t depth, uint64_t* nodes,
+                    pabi_timing_t* timing);
+/* The same for n independent roots in one pass (benches/chess.rs:49-104 loops over
+ * positions; tests/chess.rs:555-578 loops over a book): nodes_out[i] = perft(roots[i], depth). */
+int pabi_cuda_perft_batch(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, uint8_t depth,
+                          uint64_t* nodes_out, pabi_timing_t* timing);
+/* Root-subtree sharding for multi-GPU runs: the tree is expanded breadth-first to
+ * `split_ply` plies (fewer if the depth is smaller), this call then walks only
+ * the subtrees whose index in that frontier is congruent to shard_index modulo
+ * shard_count.  Summing *nodes over all shards gives perft(root, depth). */
+int pabi_cuda_perft_shard(pabi_cuda_ctx* ctx, const pabi_position_t* root, uint8_t depth,
+                          uint32_t split_ply, uint32_t shard_index, uint32_t shard_count,
+                          uint64_t* nodes, pabi_timing_t* timing);
+/* perft "divide": the root's moves in generate_moves order with the node count
+ * below each (the per-move breakdown `go perft` prints; engine/mod.rs:176-190). */
+int pabi_cuda_perft_divide(pabi_cuda_ctx* ctx, const pabi_position_t* root, uint8_t depth,
+                           pabi_move_t moves_out[PABI_MAX_MOVES], uint64_t nodes_out[PABI_MAX_MOVES],
+                           uint32_t* n_moves, pabi_timing_t* timing);
+
+/* Position::generate_moves(), src/chess/position.rs:317-408, for n positions.
+ * CSR output: the moves of position i are moves[offsets[i] .. offsets[i+1]) in the
+ * reference's order.  Returns -2 (and the required size in offsets[n]) when
+ * moves_cap is too small. */
+int pabi_cuda_generate_moves_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, size_t n,
+                                   uint32_t* offsets /* [n+1] */, pabi_move_t* moves, size_t moves_cap,
+                                   pabi_timing_t* timing);
+/* generate_moves().len() for n positions (perft's bulk count, position.rs:914-916) */
+int pabi_cuda_count_moves_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, size_t n,
+                                uint32_t* counts /* [n] */, pabi_timing_t* timing);
+/* Position::in_check(), src/chess/position.rs:735-746, for n positions */
+int pabi_cuda_in_check_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, size_t n,
+                             uint8_t* in_check /* [n] */, pabi_timing_t* timing);
+/* Position::make_move(&Move), src/chess/position.rs:414-433: out[i] = positions[i] after moves[i]
+ * (moves must be legal; the hash field is copied unchanged). */
+int pabi_cuda_make_moves_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, const pabi_move_t* moves,
+                               size_t n, pabi_position_t* out, pabi_timing_t* timing);
+/* One breadth-first ply: every child of every position, in generate_moves order
+ * (clone + make_move of position.rs:918-920).  children may be NULL to get only
+ * the offsets.  Returns -2 when children_cap is too small. */
+int pabi_cuda_expand_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, size_t n,
+                           uint32_t* offsets /* [n+1] */, pabi_position_t* children, size_t children_cap,
+                           pabi_timing_t* timing);
+
+/* ---- device-resident variants (inputs/outputs already in HBM) ------------- */
+/* Positions in the 64-byte SoA record: word w of record i at
+ * records[w * stride + i].  Used by bench.py to time the kernels without copies. */
+int pabi_cuda_pack_records(pabi_cuda_ctx* ctx, const pabi_position_t* positions, size_t n,
+                           uint64_t* device_records, size_t stride);
+int pabi_cuda_generate_moves_device(pabi_cuda_ctx* ctx, const uint64_t* device_records, size_t stride, size_t n,
+                                    uint32_t* device_offsets, pabi_move_t* device_moves, size_t moves_cap,
+                                    uint64_t* total_moves, pabi_timing_t* timing);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PABI_CUDA_H */

@@ -1,0 +1,296 @@
+"""Host-side mirror of pabi's `pabi::chess` API for the perft / move-generation path.
+
+Names and semantics follow the Rust crate (paths relative to its root):
+
+    Position::starting / from_fen / try_from / Display   src/chess/position.rs:78-91,157-275,809-860
+    Position::generate_moves / make_move / in_check       src/chess/position.rs:317-433,735-746
+    perft(&Position, depth)                               src/chess/position.rs:909-924
+    Move::{new, from_uci, from, to, promotion}, Display   src/chess/core.rs:24-134
+
+Everything that generates or makes moves runs on the GPU through the C ABI of
+`include/pabi_cuda.h`; this module only marshals buffers.  The batched entry
+points on :class:`Engine` are what a datagen / book / perft driver should use;
+the single-position methods on :class:`Position` are one-element batches.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native
+from ._native import POSITION_DTYPE, PabiCudaError, PositionStruct, Timing
+
+NO_SQUARE = 64
+STARTING_FEN = "rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1"
+
+
+class Move:
+    """16-bit packed move (src/chess/core.rs:24-66): bits 0-5 from, 6-11 to, 12-14 promotion."""
+
+    __slots__ = ("raw",)
+    PROMOTIONS = {None: 0, "n": 1, "b": 2, "r": 3, "q": 4}
+
+    def __init__(self, from_square: int, to_square: int, promotion: Optional[str] = None):
+        self.raw = (from_square & 63) | ((to_square & 63) << 6) | (self.PROMOTIONS[promotion] << 12)
+
+    @classmethod
+    def from_raw(cls, raw: int) -> "Move":
+        m = cls.__new__(cls)
+        m.raw = int(raw)
+        return m
+
+    @classmethod
+    def from_uci(cls, uci: str) -> "Move":
+        out = C.c_uint16()
+        if _native.lib().pabi_move_from_uci(uci.encode(), C.byref(out)) != 0:
+            raise ValueError(f"UCI move should be 4 or 5 characters of squares and promotion, got {uci!r}")
+        return cls.from_raw(out.value)
+
+    def from_(self) -> int:
+        return self.raw & 63
+
+    def to(self) -> int:
+        return (self.raw >> 6) & 63
+
+    def promotion(self) -> Optional[str]:
+        return (None, "n", "b", "r", "q")[(self.raw >> 12) & 7]
+
+    def __str__(self) -> str:
+        buf = C.create_string_buffer(6)
+        _native.lib().pabi_move_to_uci(self.raw, buf)
+        return buf.value.decode()
+
+    def __repr__(self) -> str:
+        return f"Move({self})"
+
+    def __eq__(self, other) -> bool:
+        return isinstance(other, Move) and other.raw == self.raw
+
+    def __hash__(self) -> int:
+        return hash(self.raw)
+
+
+def _as_array(positions) -> np.ndarray:
+    """Sequence of Position / structured array -> contiguous POSITION_DTYPE array."""
+    if isinstance(positions, np.ndarray):
+        if positions.dtype.itemsize != 112:
+            raise TypeError("positions array must have 112-byte records (pabi_position_t)")
+        return np.ascontiguousarray(positions)
+    arr = np.zeros(len(positions), dtype=POSITION_DTYPE)
+    for i, p in enumerate(positions):
+        C.memmove(arr.ctypes.data + 112 * i, C.byref(p.raw), 112)
+    return arr
+
+
+class Engine:
+    """One CUDA context of the library (`pabi_cuda_ctx`): a device, a stream, the
+    staged tables and the breadth-first frontier buffers."""
+
+    def __init__(self, device: int = -1, frontier_capacity: int = 0):
+        self._ctx = C.c_void_p()
+        L = _native.lib()
+        rc = L.pabi_cuda_create(device, frontier_capacity, C.byref(self._ctx))
+        if rc != 0:
+            raise PabiCudaError(rc, "pabi_cuda_create failed (a CUDA device is required; there is no CPU fallback)")
+        self.last_timing: Optional[Timing] = None
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            _native.lib().pabi_cuda_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def device(self) -> int:
+        return _native.lib().pabi_cuda_device(self._ctx)
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise PabiCudaError(rc, _native.lib().pabi_cuda_last_error(self._ctx).decode())
+
+    # -- perft ---------------------------------------------------------------
+    def perft(self, position: "Position", depth: int) -> int:
+        nodes, t = C.c_uint64(), Timing()
+        self._check(_native.lib().pabi_cuda_perft(self._ctx, C.byref(position.raw), depth, C.byref(nodes), C.byref(t)))
+        self.last_timing = t
+        return nodes.value
+
+    def perft_batch(self, positions, depth: int) -> np.ndarray:
+        arr = _as_array(positions)
+        out, t = np.zeros(len(arr), dtype=np.uint64), Timing()
+        self._check(_native.lib().pabi_cuda_perft_batch(self._ctx, arr.ctypes.data, len(arr), depth, out.ctypes.data,
+                                                        C.byref(t)))
+        self.last_timing = t
+        return out
+
+    def perft_shard(self, position: "Position", depth: int, split_ply: int, shard_index: int, shard_count: int) -> int:
+        nodes, t = C.c_uint64(), Timing()
+        self._check(_native.lib().pabi_cuda_perft_shard(self._ctx, C.byref(position.raw), depth, split_ply, shard_index,
+                                                        shard_count, C.byref(nodes), C.byref(t)))
+        self.last_timing = t
+        return nodes.value
+
+    def divide(self, position: "Position", depth: int) -> List[Tuple[Move, int]]:
+        moves = (C.c_uint16 * _native.MAX_MOVES)()
+        nodes = (C.c_uint64 * _native.MAX_MOVES)()
+        n, t = C.c_uint32(), Timing()
+        self._check(_native.lib().pabi_cuda_perft_divide(self._ctx, C.byref(position.raw), depth, moves, nodes, C.byref(n),
+                                                         C.byref(t)))
+        self.last_timing = t
+        return [(Move.from_raw(moves[i]), int(nodes[i])) for i in range(n.value)]
+
+    # -- batched move generation ----------------------------------------------
+    def generate_moves_batch(self, positions) -> Tuple[np.ndarray, np.ndarray]:
+        """CSR move lists: (offsets[n+1] u32, moves u16) in the reference's order."""
+        arr = _as_array(positions)
+        n = len(arr)
+        offsets = np.zeros(n + 1, dtype=np.uint32)
+        moves = np.zeros(max(64, 48 * n), dtype=np.uint16)
+        t = Timing()
+        L = _native.lib()
+        rc = L.pabi_cuda_generate_moves_batch(self._ctx, arr.ctypes.data, n, offsets.ctypes.data, moves.ctypes.data,
+                                              len(moves), C.byref(t))
+        if rc == -2:
+            moves = np.zeros(int(offsets[n]), dtype=np.uint16)
+            rc = L.pabi_cuda_generate_moves_batch(self._ctx, arr.ctypes.data, n, offsets.ctypes.data, moves.ctypes.data,
+                                                  len(moves), C.byref(t))
+        self._check(rc)
+        self.last_timing = t
+        return offsets, moves[: int(offsets[n])].copy()
+
+    def count_moves_batch(self, positions) -> np.ndarray:
+        arr = _as_array(positions)
+        out, t = np.zeros(len(arr), dtype=np.uint32), Timing()
+        self._check(_native.lib().pabi_cuda_count_moves_batch(self._ctx, arr.ctypes.data, len(arr), out.ctypes.data, C.byref(t)))
+        self.last_timing = t
+        return out
+
+    def in_check_batch(self, positions) -> np.ndarray:
+        arr = _as_array(positions)
+        out, t = np.zeros(len(arr), dtype=np.uint8), Timing()
+        self._check(_native.lib().pabi_cuda_in_check_batch(self._ctx, arr.ctypes.data, len(arr), out.ctypes.data, C.byref(t)))
+        self.last_timing = t
+        return out.astype(bool)
+
+    def make_moves_batch(self, positions, moves: Sequence[int]) -> np.ndarray:
+        arr = _as_array(positions)
+        mv = np.ascontiguousarray(np.asarray(moves, dtype=np.uint16))
+        if len(mv) != len(arr):
+            raise ValueError("one move per position")
+        out, t = np.zeros(len(arr), dtype=POSITION_DTYPE), Timing()
+        self._check(_native.lib().pabi_cuda_make_moves_batch(self._ctx, arr.ctypes.data, mv.ctypes.data, len(arr),
+                                                             out.ctypes.data, C.byref(t)))
+        self.last_timing = t
+        return out
+
+    def expand_batch(self, positions) -> Tuple[np.ndarray, np.ndarray]:
+        """Every child of every position in generate_moves order: (offsets[n+1], children)."""
+        arr = _as_array(positions)
+        n = len(arr)
+        offsets = np.zeros(n + 1, dtype=np.uint32)
+        L, t = _native.lib(), Timing()
+        self._check(L.pabi_cuda_expand_batch(self._ctx, arr.ctypes.data, n, offsets.ctypes.data, None, 0, C.byref(t)))
+        children = np.zeros(int(offsets[n]), dtype=POSITION_DTYPE)
+        if len(children):
+            self._check(L.pabi_cuda_expand_batch(self._ctx, arr.ctypes.data, n, offsets.ctypes.data, children.ctypes.data,
+                                                 len(children), C.byref(t)))
+        self.last_timing = t
+        return offsets, children
+
+
+_default_engine: Optional[Engine] = None
+
+
+def default_engine() -> Engine:
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine()
+    return _default_engine
+
+
+class Position:
+    """pabi's `Position` (src/chess/position.rs:45-63) as a 112-byte C struct."""
+
+    __slots__ = ("raw",)
+
+    def __init__(self, raw: Optional[PositionStruct] = None):
+        self.raw = raw if raw is not None else PositionStruct()
+
+    @classmethod
+    def starting(cls) -> "Position":
+        p = cls()
+        _native.lib().pabi_position_starting(C.byref(p.raw))
+        return p
+
+    @classmethod
+    def from_fen(cls, fen: str) -> "Position":
+        """Strict FEN / operation-less EPD (position.rs:157-275); raises ValueError with the reference's message."""
+        p, err = cls(), C.create_string_buffer(512)
+        if _native.lib().pabi_position_from_fen(fen.encode("utf-8"), C.byref(p.raw), err, 512) != 0:
+            raise ValueError(err.value.decode("utf-8", "replace"))
+        return p
+
+    @classmethod
+    def try_from(cls, text: str) -> "Position":
+        """`impl TryFrom<&str> for Position` (position.rs:809-821): trims, accepts a "fen "/"epd " prefix."""
+        p, err = cls(), C.create_string_buffer(512)
+        if _native.lib().pabi_position_parse(text.encode("utf-8"), C.byref(p.raw), err, 512) != 0:
+            raise ValueError(err.value.decode("utf-8", "replace"))
+        return p
+
+    @classmethod
+    def from_record(cls, record) -> "Position":
+        return cls(PositionStruct.from_buffer_copy(np.asarray(record).tobytes()))
+
+    def clone(self) -> "Position":
+        q = Position()
+        C.memmove(C.byref(q.raw), C.byref(self.raw), 112)
+        return q
+
+    def __str__(self) -> str:
+        buf = C.create_string_buffer(128)
+        _native.lib().pabi_position_to_fen(C.byref(self.raw), buf, 128)
+        return buf.value.decode()
+
+    def __repr__(self) -> str:
+        return f"Position({self})"
+
+    def __eq__(self, other) -> bool:
+        return isinstance(other, Position) and bytes(self.raw)[:96] == bytes(other.raw)[:96] and str(self) == str(other)
+
+    def us(self) -> int:
+        return self.raw.side_to_move
+
+    def they(self) -> int:
+        return self.raw.side_to_move ^ 1
+
+    def num_pieces(self) -> int:
+        return sum(bin(b).count("1") for b in list(self.raw.white) + list(self.raw.black))
+
+    def halfmove_clock_expired(self) -> bool:
+        return self.raw.halfmove_clock >= 100  # position.rs:750-752
+
+    def generate_moves(self, engine: Optional[Engine] = None) -> List[Move]:
+        _, moves = (engine or default_engine()).generate_moves_batch([self])
+        return [Move.from_raw(m) for m in moves]
+
+    def make_move(self, move: Move, engine: Optional[Engine] = None) -> None:
+        out = (engine or default_engine()).make_moves_batch([self], [move.raw])
+        hash_ = self.raw.hash
+        C.memmove(C.byref(self.raw), out.ctypes.data, 112)
+        self.raw.hash = hash_
+
+    def in_check(self, engine: Optional[Engine] = None) -> bool:
+        return bool((engine or default_engine()).in_check_batch([self])[0])
+
+
+def perft(position: Position, depth: int, engine: Optional[Engine] = None) -> int:
+    """`perft(&Position, depth) -> u64` (src/chess/position.rs:909-924) on the GPU."""
+    return (engine or default_engine()).perft(position, depth)

@@ -1,0 +1,548 @@
+/*
+ * chess.cuh -- the per-position arithmetic of the B200 perft / move-generation
+ * path: compact position record, attack analysis, counting and emitting move
+ * generators, make_move.
+ *
+ * Everything here is `__host__ __device__` so the same source is (a) inlined
+ * into the sm_100a kernels of kernels.cu and (b) compiled for the host by
+ * tests/native/hostcheck.cpp, which lets the CPU test-suite compare this exact
+ * logic with the oracle before any GPU time is spent.  The shipped library only
+ * ever calls it from kernels.
+ *
+ * Behaviour follows pabi (file:line = /root/reference/src/chess/...):
+ *   attack analysis   attacks.rs:101-200   (AttackInfo::new)
+ *   generate_moves    position.rs:317-408  (+ per-piece generators :1034-1288)
+ *   make_move         position.rs:414-732
+ *   Move packing      core.rs:24-66, promotions core.rs:700-705
+ * but is organised for a GPU thread: one 64-byte record per position, set-wise
+ * pawn generation, pins found by x-raying from the king, no move objects when
+ * only the count is needed (pabi's perft bulk-counts at depth 1,
+ * position.rs:914-916).
+ */
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PB_HD __host__ __device__ __forceinline__
+#else
+#define PB_HD inline __attribute__((always_inline))
+#endif
+
+namespace pabi {
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef uint16_t u16;
+typedef uint8_t u8;
+
+/* ---- bit helpers ------------------------------------------------------- */
+PB_HD int popc(u64 x) {
+#ifdef __CUDA_ARCH__
+  return __popcll(x);
+#else
+  return __builtin_popcountll(x);
+#endif
+}
+/* index of the least significant set bit; x != 0 (bitboard.rs:310-322 iterates LS1B first) */
+PB_HD int lsb(u64 x) {
+#ifdef __CUDA_ARCH__
+  return __ffsll((long long)x) - 1;
+#else
+  return __builtin_ctzll(x);
+#endif
+}
+PB_HD u64 bit(int sq) { return 1ULL << sq; }
+
+/* ---- constants --------------------------------------------------------- */
+constexpr u64 FILE_A = 0x0101010101010101ULL;
+constexpr u64 FILE_H = 0x8080808080808080ULL;
+constexpr u64 RANK_1 = 0x00000000000000FFULL;
+constexpr u64 RANK_3 = 0x0000000000FF0000ULL;
+constexpr u64 RANK_6 = 0x0000FF0000000000ULL;
+constexpr u64 RANK_8 = 0xFF00000000000000ULL;
+constexpr int NO_SQUARE = 64;
+
+/* Move packing, core.rs:24-66: bits 0-5 from, 6-11 to, 12-14 promotion
+ * (0 none, 1 N, 2 B, 3 R, 4 Q; core.rs:700-705). */
+constexpr int PROMO_N = 1, PROMO_B = 2, PROMO_R = 3, PROMO_Q = 4;
+PB_HD u16 pack_move(int from, int to, int promo) { return (u16)(from | (to << 6) | (promo << 12)); }
+
+/* ---- the 64-byte device record --------------------------
+ * word 0 white occupancy, words 1..6 pawns, knights, bishops, rooks, queens,
+ * kings (both colours merged), word 7 meta:
+ *   bits 0-3 castling (core.rs:604-612: 1 K, 2 Q, 4 k, 8 q), bits 4-10 en
+ *   passant square (64 = none), bit 11 side to move (0 white), bits 16-23
+ *   halfmove clock, bits 32-47 fullmove counter.
+ * In HBM the records are stored SoA: word w of record i lives at
+ * base[w * stride + i], so a warp reads/writes 256 contiguous bytes per word. */
+struct Pos {
+  u64 white, pawns, knights, bishops, rooks, queens, kings, meta;
+};
+constexpr int POS_WORDS = 8;
+
+PB_HD int meta_castling(u64 m) { return (int)(m & 15); }
+PB_HD int meta_ep(u64 m) { return (int)((m >> 4) & 127); }
+PB_HD int meta_stm(u64 m) { return (int)((m >> 11) & 1); }
+PB_HD int meta_halfmove(u64 m) { return (int)((m >> 16) & 255); }
+PB_HD int meta_fullmove(u64 m) { return (int)((m >> 32) & 0xFFFF); }
+PB_HD u64 make_meta(int castling, int ep, int stm, int halfmove, int fullmove) {
+  return (u64)castling | ((u64)ep << 4) | ((u64)stm << 11) | ((u64)halfmove << 16) |
+         ((u64)fullmove << 32);
+}
+
+PB_HD Pos load_pos(const u64* __restrict__ base, size_t stride, size_t i) {
+  Pos p;
+  p.white = base[0 * stride + i];
+  p.pawns = base[1 * stride + i];
+  p.knights = base[2 * stride + i];
+  p.bishops = base[3 * stride + i];
+  p.rooks = base[4 * stride + i];
+  p.queens = base[5 * stride + i];
+  p.kings = base[6 * stride + i];
+  p.meta = base[7 * stride + i];
+  return p;
+}
+PB_HD void store_pos(u64* __restrict__ base, size_t stride, size_t i, const Pos& p) {
+  base[0 * stride + i] = p.white;
+  base[1 * stride + i] = p.pawns;
+  base[2 * stride + i] = p.knights;
+  base[3 * stride + i] = p.bishops;
+  base[4 * stride + i] = p.rooks;
+  base[5 * stride + i] = p.queens;
+  base[6 * stride + i] = p.kings;
+  base[7 * stride + i] = p.meta;
+}
+
+/* ---- tables ------------------------------------------------------------
+ * Same contents as pabi's generated tables (generated.rs:30-82), regenerated
+ * from their definition on the host (tables.cpp):
+ *  - leaper tables and the bishop attack table (pabi's 5 248 entries, per-square
+ *    blocks at pabi's offsets; inside a block the entries are addressed by a
+ *    multiply-shift hash instead of PEXT, which sm_100a does not have) live in
+ *    shared memory, staged once per block;
+ *  - the rook attack table (pabi's 102 400 entries, 800 KB) and RAYS (32 KB) stay
+ *    in global memory and are read through L1 (ld.global.nc).
+ * `SliderEntry` is one 16-byte shared-memory load. */
+struct SliderEntry {
+  u64 mask;  /* relevant occupancy, generated/..._relevant_occupancies.rs */
+  u64 magic; /* index = offset + (((occ & mask) * magic) >> (64 - bits)) */
+};
+constexpr int BISHOP_TABLE_SIZE = 5248;  /* generated.rs:30 */
+constexpr int ROOK_TABLE_SIZE = 102400; /* generated.rs:44 */
+
+struct SharedTables {
+  u64 knight[64];
+  u64 king[64];
+  u64 diag[64]; /* full a1-h8-direction line through the square (square included) */
+  u64 anti[64]; /* full a8-h1-direction line through the square */
+  SliderEntry bishop[64];
+  SliderEntry rook[64];
+  u32 bishop_os[64]; /* offset | (32 - bits) << 24 */
+  u32 rook_os[64];
+  u8 keep_from[64]; /* castling rights kept when a move leaves this square (position.rs:435-468) */
+  u8 keep_to[64];   /* ... when a move lands on this square */
+  u64 bishop_attacks[BISHOP_TABLE_SIZE];
+};
+
+struct GlobalTables {
+  const u64* rook_attacks; /* [ROOK_TABLE_SIZE] */
+  const u64* rays;         /* [64*64], attacks.rs:54-56: [from, to) on a common line, else 0 */
+};
+
+PB_HD u64 ldg64(const u64* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg((const unsigned long long*)p);
+#else
+  return *p;
+#endif
+}
+
+struct Tables {
+  const SharedTables* s;
+  GlobalTables g;
+
+  PB_HD u64 knight(int sq) const { return s->knight[sq]; }
+  PB_HD u64 king(int sq) const { return s->king[sq]; }
+  /* attacks.rs:35-41 */
+  PB_HD u64 bishop(int sq, u64 occ) const {
+    SliderEntry e = s->bishop[sq];
+    u32 os = s->bishop_os[sq];
+    u32 h = (u32)(((occ & e.mask) * e.magic) >> 32);
+    return s->bishop_attacks[(os & 0xFFFFFFu) + (h >> (os >> 24))];
+  }
+  /* attacks.rs:27-33 */
+  PB_HD u64 rook(int sq, u64 occ) const {
+    SliderEntry e = s->rook[sq];
+    u32 os = s->rook_os[sq];
+    u32 h = (u32)(((occ & e.mask) * e.magic) >> 32);
+    return ldg64(g.rook_attacks + (os & 0xFFFFFFu) + (h >> (os >> 24)));
+  }
+  /* attacks.rs:54-56 */
+  PB_HD u64 ray(int from, int to) const { return ldg64(g.rays + from * 64 + to); }
+  /* The full line through `king` and `sq` (they are known to be aligned). */
+  PB_HD u64 line(int king, int sq) const {
+    if ((king >> 3) == (sq >> 3)) return RANK_1 << (king & 56);
+    if ((king & 7) == (sq & 7)) return FILE_A << (king & 7);
+    u64 d = s->diag[king];
+    return ((d >> sq) & 1) ? d : s->anti[king];
+  }
+};
+
+/* Pawn capture targets of a set of pawns (generated white/black_pawn_attacks.rs
+ * hold the same per-square sets; pawns never stand on ranks 1/8). */
+PB_HD u64 pawn_attacks_west(u64 pawns, int colour) { /* towards file a */
+  return colour == 0 ? (pawns & ~FILE_A) << 7 : (pawns & ~FILE_A) >> 9;
+}
+PB_HD u64 pawn_attacks_east(u64 pawns, int colour) { /* towards file h */
+  return colour == 0 ? (pawns & ~FILE_H) << 9 : (pawns & ~FILE_H) >> 7;
+}
+PB_HD u64 pawn_attacks(u64 pawns, int colour) {
+  return pawn_attacks_west(pawns, colour) | pawn_attacks_east(pawns, colour);
+}
+PB_HD u64 push(u64 b, int colour) { return colour == 0 ? b << 8 : b >> 8; }
+PB_HD u64 unpush(u64 b, int colour) { return colour == 0 ? b >> 8 : b << 8; }
+
+/* ---- attack analysis (attacks.rs:101-200) ------------------------------ */
+struct Analysis {
+  u64 our, their, occ;
+  u64 safe_king;  /* AttackInfo::safe_king_squares */
+  u64 checkers;   /* AttackInfo::checkers */
+  u64 pins;       /* AttackInfo::pins */
+  u64 attacks;    /* AttackInfo::attacks, sliders seen through our king (see below) */
+  u64 block;      /* blocking_ray of position.rs:333-353; 0 when doubly checked */
+  int us, king;
+};
+
+/* Differences from the reference's loop, none observable:
+ *  - sliders look through our king (occupancy without it) for every slider,
+ *    not only for checking ones: a slider's attack set changes when the king is
+ *    removed only if the king is in it, i.e. only for checkers, and for those
+ *    the reference subtracts exactly that extended set (attacks.rs:143,163,183).
+ *    `attacks` is only used for castling, which requires no checkers, where both
+ *    definitions coincide.
+ *  - pins are found from the king: our first blockers on its lines, then the
+ *    enemy sliders that appear when they are removed; "exactly one blocker and
+ *    it is ours" (attacks.rs:147-156) is the same condition.
+ *  - xrays (attacks.rs:93) are not computed: move generation never reads them. */
+template <class TB>
+PB_HD void analyze(const Pos& p, const TB& tb, Analysis& a) {
+  const int us = meta_stm(p.meta);
+  const int them = us ^ 1;
+  const u64 occ = p.pawns | p.knights | p.bishops | p.rooks | p.queens | p.kings;
+  const u64 our = us == 0 ? p.white : occ & ~p.white;
+  const u64 their = occ ^ our;
+  const u64 king_bb = p.kings & our;
+  const int king = lsb(king_bb);
+  const u64 occ_nk = occ ^ king_bb;
+  const u64 their_diag = (p.bishops | p.queens) & their;
+  const u64 their_orth = (p.rooks | p.queens) & their;
+
+  u64 att = tb.king(lsb(p.kings & their));
+  att |= pawn_attacks(p.pawns & their, them);
+  for (u64 b = p.knights & their; b; b &= b - 1) att |= tb.knight(lsb(b));
+  for (u64 b = their_diag; b; b &= b - 1) att |= tb.bishop(lsb(b), occ_nk);
+  for (u64 b = their_orth; b; b &= b - 1) att |= tb.rook(lsb(b), occ_nk);
+
+  const u64 king_diag = tb.bishop(king, occ);
+  const u64 king_orth = tb.rook(king, occ);
+  u64 checkers = (tb.knight(king) & p.knights & their) |
+                 (pawn_attacks(king_bb, us) & p.pawns & their) | (king_diag & their_diag) |
+                 (king_orth & their_orth);
+
+  u64 pins = 0;
+  {
+    const u64 cand = king_diag & our;
+    if (cand) {
+      u64 pinners = tb.bishop(king, occ ^ cand) & ~king_diag & their_diag;
+      for (; pinners; pinners &= pinners - 1) pins |= tb.ray(lsb(pinners), king) & cand;
+    }
+  }
+  {
+    const u64 cand = king_orth & our;
+    if (cand) {
+      u64 pinners = tb.rook(king, occ ^ cand) & ~king_orth & their_orth;
+      for (; pinners; pinners &= pinners - 1) pins |= tb.ray(lsb(pinners), king) & cand;
+    }
+  }
+
+  a.us = us;
+  a.king = king;
+  a.our = our;
+  a.their = their;
+  a.occ = occ;
+  a.attacks = att;
+  a.safe_king = tb.king(king) & ~our & ~att;
+  a.checkers = checkers;
+  a.pins = pins;
+  /* position.rs:333-358 */
+  if (checkers == 0) {
+    a.block = ~0ULL;
+  } else if ((checkers & (checkers - 1)) == 0) {
+    u64 r = tb.ray(lsb(checkers), king);
+    a.block = r ? r : checkers;
+  } else {
+    a.block = 0;
+  }
+}
+
+/* position.rs:1226-1288 with the walk masks of attacks.rs:203-214.  Returns a
+ * 2-bit set: bit 0 short, bit 1 long. */
+PB_HD int castle_moves(const Pos& p, const Analysis& a) {
+  if (a.checkers) return 0;
+  const int rights = meta_castling(p.meta) >> (2 * a.us);
+  const int sh = 56 * a.us;
+  int r = 0;
+  if ((rights & 1) && ((a.attacks | a.occ) & (0x60ULL << sh)) == 0) r |= 1;
+  if ((rights & 2) && (a.attacks & (0x0CULL << sh)) == 0 && (a.occ & (0x0EULL << sh)) == 0) r |= 2;
+  return r;
+}
+
+/* En passant (position.rs:1144-1178).  Returns the set of our pawns that may
+ * capture on the en passant square. */
+template <class TB>
+PB_HD u64 en_passant_sources(const Pos& p, const TB& tb, const Analysis& a) {
+  const int ep = meta_ep(p.meta);
+  if (ep >= NO_SQUARE) return 0;
+  const int them = a.us ^ 1;
+  const u64 ep_bb = bit(ep);
+  const u64 candidates = pawn_attacks(ep_bb, them) & p.pawns & a.our;
+  if (!candidates) return 0;
+  const u64 ep_pawn = push(ep_bb, them); /* the pushed pawn */
+  if (a.checkers & ep_pawn) return candidates & ~a.pins;
+  const u64 their_diag = (p.bishops | p.queens) & a.their;
+  const u64 their_orth = (p.rooks | p.queens) & a.their;
+  u64 ok = 0;
+  for (u64 b = candidates; b; b &= b - 1) {
+    const u64 cand = b & (0 - b);
+    const u64 after = ((a.occ & ~cand) & ~ep_pawn) | ep_bb;
+    if ((tb.bishop(a.king, after) & their_diag) == 0 && (tb.rook(a.king, after) & their_orth) == 0)
+      ok |= cand;
+  }
+  return ok;
+}
+
+/* Pawn source sets after the pin filter (position.rs:1128,1200,1217 applied
+ * set-wise): a pinned pawn may push only along the king's file and capture only
+ * along the pin diagonal. */
+struct PawnSets {
+  u64 west, east, pushers;
+};
+template <class TB>
+PB_HD PawnSets pawn_sources(const Pos& p, const TB& tb, const Analysis& a) {
+  const u64 pawns = p.pawns & a.our;
+  const u64 free_pawns = pawns & ~a.pins;
+  const u64 pinned = pawns & a.pins;
+  PawnSets s;
+  s.west = s.east = s.pushers = free_pawns;
+  if (pinned) {
+    const u64 d = tb.s->diag[a.king], an = tb.s->anti[a.king];
+    s.pushers |= pinned & (FILE_A << (a.king & 7));
+    /* white: west capture (+7) runs along the anti-diagonal, east (+9) along the
+     * diagonal; black: west (-9) along the diagonal, east (-7) along the anti-diagonal */
+    s.west |= pinned & (a.us == 0 ? an : d);
+    s.east |= pinned & (a.us == 0 ? d : an);
+  }
+  return s;
+}
+
+/* ---- count only: == generate_moves().len() (position.rs:914-916) -------- */
+template <class TB>
+PB_HD u32 count_moves(const Pos& p, const TB& tb) {
+  Analysis a;
+  analyze(p, tb, a);
+  u32 n = popc(a.safe_king);
+  if (a.block == 0) return n; /* double check: king moves only, position.rs:356 */
+  const u64 targets = ~a.our & a.block;
+
+  for (u64 b = p.knights & a.our & ~a.pins; b; b &= b - 1) n += popc(tb.knight(lsb(b)) & targets);
+  for (u64 b = (p.rooks | p.queens) & a.our; b; b &= b - 1) {
+    const int from = lsb(b);
+    u64 t = tb.rook(from, a.occ) & targets;
+    if ((a.pins >> from) & 1) t &= tb.line(a.king, from);
+    n += popc(t);
+  }
+  for (u64 b = (p.bishops | p.queens) & a.our; b; b &= b - 1) {
+    const int from = lsb(b);
+    u64 t = tb.bishop(from, a.occ) & targets;
+    if ((a.pins >> from) & 1) t &= tb.line(a.king, from);
+    n += popc(t);
+  }
+
+  const PawnSets ps = pawn_sources(p, tb, a);
+  const u64 last_rank = a.us == 0 ? RANK_8 : RANK_1;
+  const u64 capture_targets = a.their & a.block;
+  const u64 west = pawn_attacks_west(ps.west, a.us) & capture_targets;
+  const u64 east = pawn_attacks_east(ps.east, a.us) & capture_targets;
+  const u64 empty = ~a.occ;
+  const u64 single_all = push(ps.pushers, a.us) & empty;
+  const u64 single = single_all & a.block;
+  const u64 dbl = push(single_all & (a.us == 0 ? RANK_3 : RANK_6), a.us) & empty & a.block;
+  n += popc(west) + popc(east) + popc(single) + popc(dbl);
+  const u64 promos = (west | single) & last_rank;
+  if (promos | (east & last_rank))
+    n += 3 * (popc(west & last_rank) + popc(east & last_rank) + popc(single & last_rank));
+  if (meta_ep(p.meta) < NO_SQUARE) n += popc(en_passant_sources(p, tb, a));
+  const int c = castle_moves(p, a);
+  n += (c & 1) + (c >> 1);
+  return n;
+}
+
+/* ---- ordered generation (position.rs:317-408; order of SURVEY.md A.3) ---
+ * emit(from, to, promotion) is called once per legal move in the reference's
+ * order.  Returns the number of moves. */
+template <class TB, class Emit>
+PB_HD u32 generate_moves(const Pos& p, const TB& tb, Emit&& emit) {
+  Analysis a;
+  analyze(p, tb, a);
+  u32 n = 0;
+  /* generate_king_moves, position.rs:1034-1040 */
+  for (u64 t = a.safe_king; t; t &= t - 1, ++n) emit(a.king, lsb(t), 0);
+  if (a.block == 0) return n;
+  const u64 targets = ~a.our & a.block;
+
+  /* generate_knight_moves, position.rs:1042-1059 */
+  for (u64 b = p.knights & a.our & ~a.pins; b; b &= b - 1) {
+    const int from = lsb(b);
+    for (u64 t = tb.knight(from) & targets; t; t &= t - 1, ++n) emit(from, lsb(t), 0);
+  }
+  /* generate_rook_moves over rooks|queens, position.rs:1061-1081 */
+  for (u64 b = (p.rooks | p.queens) & a.our; b; b &= b - 1) {
+    const int from = lsb(b);
+    u64 t = tb.rook(from, a.occ) & targets;
+    if ((a.pins >> from) & 1) t &= tb.line(a.king, from);
+    for (; t; t &= t - 1, ++n) emit(from, lsb(t), 0);
+  }
+  /* generate_bishop_moves over bishops|queens, position.rs:1083-1104 */
+  for (u64 b = (p.bishops | p.queens) & a.our; b; b &= b - 1) {
+    const int from = lsb(b);
+    u64 t = tb.bishop(from, a.occ) & targets;
+    if ((a.pins >> from) & 1) t &= tb.line(a.king, from);
+    for (; t; t &= t - 1, ++n) emit(from, lsb(t), 0);
+  }
+
+  /* generate_pawn_moves, position.rs:1106-1224 */
+  const PawnSets ps = pawn_sources(p, tb, a);
+  const int last_rank = a.us == 0 ? 7 : 0;
+  const u64 capture_targets = a.their & a.block;
+  /* captures: per pawn ascending, per target ascending (:1123-1142) */
+  for (u64 b = ps.west | ps.east; b; b &= b - 1) {
+    const u64 from_bb = b & (0 - b);
+    const int from = lsb(b);
+    u64 t = (pawn_attacks_west(from_bb & ps.west, a.us) | pawn_attacks_east(from_bb & ps.east, a.us)) &
+            capture_targets;
+    for (; t; t &= t - 1) {
+      const int to = lsb(t);
+      if ((to >> 3) == last_rank) {
+        emit(from, to, PROMO_Q), emit(from, to, PROMO_R), emit(from, to, PROMO_B), emit(from, to, PROMO_N);
+        n += 4;
+      } else {
+        emit(from, to, 0), ++n;
+      }
+    }
+  }
+  /* en passant (:1144-1178) */
+  if (meta_ep(p.meta) < NO_SQUARE)
+    for (u64 b = en_passant_sources(p, tb, a); b; b &= b - 1, ++n) emit(lsb(b), meta_ep(p.meta), 0);
+  /* single pushes in ascending target order (:1180-1204) */
+  const u64 empty = ~a.occ;
+  const u64 single_all = push(ps.pushers, a.us) & empty;
+  const int back = a.us == 0 ? -8 : 8;
+  for (u64 t = single_all & a.block; t; t &= t - 1) {
+    const int to = lsb(t);
+    if ((to >> 3) == last_rank) {
+      emit(to + back, to, PROMO_Q), emit(to + back, to, PROMO_R), emit(to + back, to, PROMO_B),
+          emit(to + back, to, PROMO_N);
+      n += 4;
+    } else {
+      emit(to + back, to, 0), ++n;
+    }
+  }
+  /* double pushes in ascending target order (:1205-1223) */
+  for (u64 t = push(single_all & (a.us == 0 ? RANK_3 : RANK_6), a.us) & empty & a.block; t; t &= t - 1, ++n)
+    emit(lsb(t) + 2 * back, lsb(t), 0);
+  /* generate_castle_moves: short, then long (:1236-1286) */
+  const int c = castle_moves(p, a);
+  const int home = 4 + 56 * a.us;
+  if (c & 1) emit(home, home + 2, 0), ++n;
+  if (c & 2) emit(home, home - 2, 0), ++n;
+  return n;
+}
+
+/* ---- make_move (position.rs:414-433 and helpers :435-732) --------------- */
+template <class TB>
+PB_HD void make_move(Pos& p, const TB& tb, u16 mv) {
+  const int from = mv & 63, to = (mv >> 6) & 63, promo = (mv >> 12) & 7;
+  const u64 fb = bit(from), tbit = bit(to);
+  const int us = meta_stm(p.meta);
+  int castling = meta_castling(p.meta);
+  const int prev_ep = meta_ep(p.meta);
+  int halfmove = (meta_halfmove(p.meta) + 1) & 255; /* :419, u8 */
+  int fullmove = meta_fullmove(p.meta);
+  int ep = NO_SQUARE;
+
+  /* update_castling_rights, :435-468 */
+  castling &= tb.s->keep_from[from] & tb.s->keep_to[to];
+
+  const u64 occ = p.pawns | p.knights | p.bishops | p.rooks | p.queens | p.kings;
+  const u64 our = us == 0 ? p.white : occ & ~p.white;
+  u64 white = p.white;
+
+  /* handle_capture, :470-502 (a king is never captured) */
+  if ((occ & ~our) & tbit) {
+    halfmove = 0;
+    p.pawns &= ~tbit, p.knights &= ~tbit, p.bishops &= ~tbit, p.rooks &= ~tbit, p.queens &= ~tbit;
+    white &= ~tbit;
+  }
+
+  if (p.pawns & fb) { /* make_pawn_move, :504-618 */
+    halfmove = 0;
+    if (to == prev_ep) { /* prev_ep == 64 never equals a square */
+      const u64 captured = bit((to & 7) + (from & 56));
+      p.pawns &= ~captured;
+      white &= ~captured;
+    }
+    p.pawns ^= fb;
+    if (promo) {
+      if (promo == PROMO_Q) p.queens |= tbit;
+      else if (promo == PROMO_R) p.rooks |= tbit;
+      else if (promo == PROMO_B) p.bishops |= tbit;
+      else p.knights |= tbit;
+    } else {
+      p.pawns |= tbit;
+      /* :606-615: the en passant square is recorded only when an enemy pawn attacks it */
+      if ((from ^ to) == 16) {
+        const u64 skipped = bit((from + to) >> 1);
+        if (pawn_attacks(skipped, us) & p.pawns & ~our & ~fb) ep = (from + to) >> 1;
+      }
+    }
+  } else if (p.kings & fb) { /* make_king_move, :622-698 */
+    const int backrank = 56 * us;
+    if (from == backrank + 4 && (to & 56) == backrank) {
+      u64 rook_move = 0;
+      if ((to & 7) == 6) rook_move = (0xA0ULL) << backrank;      /* h -> f */
+      else if ((to & 7) == 2) rook_move = (0x09ULL) << backrank; /* a -> d */
+      /* the reference clears OUR rook on the home square (if there is one: the
+       * castling right is trusted, :632-678) and puts a rook on the target square */
+      if (rook_move) {
+        const u64 home = rook_move & (0x81ULL << backrank), dest = rook_move ^ home;
+        const u64 our_home_rook = p.rooks & our & home;
+        p.rooks = (p.rooks ^ our_home_rook) | dest;
+        if (us == 0) white = (white ^ our_home_rook) | dest;
+      }
+    }
+    p.kings ^= fb | tbit;
+  } else { /* make_regular_move, :700-732 */
+    const u64 m = fb | tbit;
+    if (p.queens & fb) p.queens ^= m;
+    else if (p.rooks & fb) p.rooks ^= m;
+    else if (p.bishops & fb) p.bishops ^= m;
+    else if (p.knights & fb) p.knights ^= m;
+  }
+  if (us == 0) white = (white & ~fb) | tbit;
+  p.white = white;
+  if (us == 1) fullmove = (fullmove + 1) & 0xFFFF; /* :428-430 */
+  p.meta = make_meta(castling, ep, us ^ 1, halfmove, fullmove);
+}
+
+} /* namespace pabi */

@@ -1,0 +1,668 @@
+/*
+ * engine.cu -- host driver of the device path and the `pabi_cuda_*` C ABI
+ * (include/pabi_cuda.h).
+ *
+ * perft (position.rs:909-924) is organised as a chunked breadth-first search:
+ * the plies above the last two are materialised level by level in HBM as SoA
+ * frontiers (count -> scan -> expand, children in the reference's move order);
+ * the last two plies run in the fused kernel k_leaf2 which never writes its
+ * children out.  A level whose children would not fit the next level's buffer
+ * is cut into chunks, each finished depth-first before the next starts, so
+ * memory use is bounded by depth * capacity whatever the tree size.
+ *
+ * There is no CPU implementation of move generation in this library: without a
+ * CUDA device every entry point here fails with the CUDA error code.
+ */
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/pabi_cuda.h"
+#include "kernels.cuh"
+#include "tables.h"
+
+using namespace pabi;
+
+namespace {
+
+constexpr size_t DEFAULT_CAPACITY = size_t(32) << 20; /* records per level buffer */
+constexpr int MAX_LEVELS = 24;
+
+struct Level {
+  u64* rec = nullptr;
+  u32* roots = nullptr;
+  u32* counts = nullptr;
+  u64* prefix = nullptr;
+  size_t cap = 0;
+};
+
+struct Buffer {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+} /* namespace */
+
+struct pabi_cuda_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  size_t capacity = DEFAULT_CAPACITY;
+  DeviceTables dt{};
+  void* d_tables = nullptr;
+  u64* d_rook = nullptr;
+  u64* d_rays = nullptr;
+  Level levels[MAX_LEVELS];
+  Level spare; /* shard gather target */
+  u64* d_tile_sums = nullptr;
+  size_t tile_sums_cap = 0;
+  u64* d_result = nullptr; /* {end, children} of k_chunk_end */
+  unsigned long long* d_visited = nullptr; /* statistics: children generated inside k_tile<LEAF> */
+  u64* h_result = nullptr; /* pinned */
+  unsigned long long* d_nodes = nullptr;
+  size_t nodes_cap = 0;
+  Buffer scratch[6];
+  std::string error;
+  /* per-call statistics */
+  uint64_t launches = 0, interior = 0;
+};
+
+namespace {
+
+struct CudaFail {
+  cudaError_t code;
+};
+
+#define CK(expr)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      ctx->error = std::string(#expr) + ": " + cudaGetErrorString(e_);                       \
+      throw CudaFail{e_};                                                                     \
+    }                                                                                         \
+  } while (0)
+
+#define LAUNCHED()                      \
+  do {                                  \
+    ++ctx->launches;                    \
+    CK(cudaGetLastError());             \
+  } while (0)
+
+int grid_for(const pabi_cuda_ctx* ctx, size_t n, int threads, int per_sm) {
+  size_t blocks = (n + threads - 1) / threads;
+  size_t cap = (size_t)ctx->sm_count * per_sm;
+  if (blocks > cap) blocks = cap;
+  return blocks ? (int)blocks : 1;
+}
+
+void* ensure(pabi_cuda_ctx* ctx, int slot, size_t bytes) {
+  Buffer& b = ctx->scratch[slot];
+  if (b.bytes < bytes) {
+    if (b.ptr) CK(cudaFree(b.ptr));
+    b.ptr = nullptr, b.bytes = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    CK(cudaMalloc(&b.ptr, want));
+    b.bytes = want;
+  }
+  return b.ptr;
+}
+
+void alloc_level(pabi_cuda_ctx* ctx, Level& l, size_t cap) {
+  if (l.cap >= cap) return;
+  if (l.rec) cudaFree(l.rec), cudaFree(l.roots), cudaFree(l.counts), cudaFree(l.prefix);
+  l = Level();
+  CK(cudaMalloc(&l.rec, cap * POS_WORDS * sizeof(u64)));
+  CK(cudaMalloc(&l.roots, cap * sizeof(u32)));
+  CK(cudaMalloc(&l.counts, cap * sizeof(u32)));
+  CK(cudaMalloc(&l.prefix, (cap + 1) * sizeof(u64)));
+  l.cap = cap;
+}
+
+Frontier frontier_of(const Level& l) { return Frontier{l.rec, l.roots, l.cap}; }
+
+void ensure_nodes(pabi_cuda_ctx* ctx, size_t n) {
+  if (ctx->nodes_cap >= n) return;
+  if (ctx->d_nodes) CK(cudaFree(ctx->d_nodes));
+  ctx->d_nodes = nullptr;
+  CK(cudaMalloc(&ctx->d_nodes, n * sizeof(unsigned long long)));
+  ctx->nodes_cap = n;
+}
+
+constexpr size_t FLAT_SMEM = sizeof(SharedTables);
+constexpr size_t TILE_SMEM = sizeof(TileShared);
+
+/* counts[0..n) of records [first, first+n) of `l`, then prefix[0..n] */
+void count_and_scan(pabi_cuda_ctx* ctx, const u64* rec, size_t stride, size_t first, size_t n, u32* counts, u64* prefix) {
+  k_count<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, rec, stride, first, n, counts);
+  LAUNCHED();
+  const size_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (ctx->tile_sums_cap < tiles) {
+    if (ctx->d_tile_sums) CK(cudaFree(ctx->d_tile_sums));
+    ctx->d_tile_sums = nullptr;
+    CK(cudaMalloc(&ctx->d_tile_sums, (tiles + 1024) * sizeof(u64)));
+    ctx->tile_sums_cap = tiles + 1024;
+  }
+  k_scan_reduce<<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(counts, n, ctx->d_tile_sums);
+  LAUNCHED();
+  k_scan_spine<<<1, 1024, 0, ctx->stream>>>(ctx->d_tile_sums, tiles);
+  LAUNCHED();
+  k_scan_down<<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(counts, n, ctx->d_tile_sums, prefix);
+  LAUNCHED();
+}
+
+template <bool LEAF>
+void launch_tile(pabi_cuda_ctx* ctx, bool multi, Frontier in, size_t first, size_t n, const u64* prefix, Frontier out) {
+  const int grid = grid_for(ctx, n, TILE_THREADS, 2);
+  if (multi)
+    k_tile<LEAF, true><<<grid, TILE_THREADS, TILE_SMEM, ctx->stream>>>(ctx->dt, in, first, n, prefix, out, ctx->d_nodes, ctx->d_visited);
+  else
+    k_tile<LEAF, false><<<grid, TILE_THREADS, TILE_SMEM, ctx->stream>>>(ctx->dt, in, first, n, prefix, out, ctx->d_nodes, ctx->d_visited);
+  LAUNCHED();
+}
+
+/* Walks `remaining` plies below the n records of level `lv`, adding leaf counts
+ * to d_nodes (per root when multi). */
+void descend(pabi_cuda_ctx* ctx, int lv, size_t n, int remaining, bool multi) {
+  if (n == 0) return;
+  Level& cur = ctx->levels[lv];
+  ctx->interior += n;
+  if (remaining == 1) {
+    const int grid = grid_for(ctx, n, FLAT_THREADS, 4);
+    if (multi)
+      k_count_accumulate<true><<<grid, FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, frontier_of(cur), n, ctx->d_nodes);
+    else
+      k_count_accumulate<false><<<grid, FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, frontier_of(cur), n, ctx->d_nodes);
+    LAUNCHED();
+    return;
+  }
+  if (remaining == 2) {
+    launch_tile<true>(ctx, multi, frontier_of(cur), 0, n, nullptr, Frontier{nullptr, nullptr, 0});
+    /* the children are generated and counted inside the kernel */
+    return;
+  }
+  if (lv + 1 >= MAX_LEVELS) {
+    ctx->error = "perft depth exceeds the supported number of breadth-first levels";
+    throw CudaFail{cudaErrorInvalidValue};
+  }
+  Level& next = ctx->levels[lv + 1];
+  alloc_level(ctx, next, ctx->capacity);
+  count_and_scan(ctx, cur.rec, cur.cap, 0, n, cur.counts, cur.prefix);
+  size_t start = 0;
+  while (start < n) {
+    k_chunk_end<<<1, 1, 0, ctx->stream>>>(cur.prefix, start, n, (u64)next.cap, ctx->d_result);
+    LAUNCHED();
+    CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result, 2 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t end = (size_t)ctx->h_result[0];
+    const size_t children = (size_t)ctx->h_result[1];
+    if (end == start) {
+      ctx->error = "frontier capacity is smaller than one position's move list";
+      throw CudaFail{cudaErrorInvalidValue};
+    }
+    if (children) {
+      launch_tile<false>(ctx, multi, frontier_of(cur), start, end - start, cur.prefix, frontier_of(next));
+      descend(ctx, lv + 1, children, remaining - 1, multi);
+    }
+    start = end;
+  }
+}
+
+struct CallTimer {
+  pabi_cuda_ctx* ctx;
+  std::chrono::steady_clock::time_point t0;
+  explicit CallTimer(pabi_cuda_ctx* c) : ctx(c), t0(std::chrono::steady_clock::now()) {
+    ctx->launches = 0, ctx->interior = 0;
+    ctx->error.clear();
+  }
+  void begin_device() { CK(cudaEventRecord(ctx->ev0, ctx->stream)); }
+  void end_device() { CK(cudaEventRecord(ctx->ev1, ctx->stream)); }
+  void finish(pabi_timing_t* t, uint64_t bytes) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (!t) return;
+    std::memset(t, 0, sizeof *t);
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    t->device_ms = ms;
+    t->host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    t->algorithmic_bytes = bytes;
+    t->kernel_launches = ctx->launches;
+    t->interior_nodes = ctx->interior;
+  }
+};
+
+/* Upload n positions (host AoS) into level 0 as SoA with roots = index. */
+void upload_roots(pabi_cuda_ctx* ctx, const pabi_position_t* pos, size_t n) {
+  alloc_level(ctx, ctx->levels[0], n > 4096 ? n : 4096);
+  void* staging = ensure(ctx, 0, n * sizeof(pabi_position_t));
+  CK(cudaMemcpyAsync(staging, pos, n * sizeof(pabi_position_t), cudaMemcpyHostToDevice, ctx->stream));
+  Level& l0 = ctx->levels[0];
+  k_pack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>((const PositionImage*)staging, n, l0.rec, l0.cap, 0, l0.roots);
+  LAUNCHED();
+}
+
+int fail(pabi_cuda_ctx* ctx, const CudaFail& f) {
+  if (ctx->error.empty()) ctx->error = cudaGetErrorString(f.code);
+  cudaGetLastError();
+  return (int)f.code;
+}
+
+int bad_arg(pabi_cuda_ctx* ctx, const char* what) {
+  if (ctx) ctx->error = what;
+  return -1;
+}
+
+int perft_impl(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, int depth, uint64_t* nodes_out, bool multi,
+               uint32_t split_ply, uint32_t shard_index, uint32_t shard_count, pabi_timing_t* timing) {
+  try {
+    CK(cudaSetDevice(ctx->device));
+    CallTimer timer(ctx);
+    if (depth == 0) {
+      for (size_t i = 0; i < n; i++) nodes_out[i] = (shard_index == 0) ? 1 : 0;
+      timer.begin_device(), timer.end_device();
+      timer.finish(timing, 0);
+      return 0;
+    }
+    const size_t n_out = multi ? n : 1;
+    ensure_nodes(ctx, n_out);
+    upload_roots(ctx, roots, n);
+    timer.begin_device();
+    CK(cudaMemsetAsync(ctx->d_nodes, 0, n_out * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_visited, 0, sizeof(unsigned long long), ctx->stream));
+    if (shard_count <= 1) {
+      descend(ctx, 0, n, depth, multi);
+    } else {
+      /* breadth-first to the split ply (at most depth - 1 so that one ply is left), whole levels only */
+      int remaining = depth;
+      int lv = 0;
+      size_t cnt = n;
+      int plies = (int)split_ply;
+      if (plies > depth - 1) plies = depth - 1;
+      for (int s = 0; s < plies && cnt; s++) {
+        Level& cur = ctx->levels[lv];
+        Level& next = ctx->levels[lv + 1];
+        count_and_scan(ctx, cur.rec, cur.cap, 0, cnt, cur.counts, cur.prefix);
+        CK(cudaMemcpyAsync(ctx->h_result, cur.prefix + cnt, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const size_t children = (size_t)ctx->h_result[0];
+        if (children > ctx->capacity) {
+          ctx->error = "split_ply frontier exceeds the frontier capacity";
+          throw CudaFail{cudaErrorInvalidValue};
+        }
+        alloc_level(ctx, next, ctx->capacity);
+        if (children) launch_tile<false>(ctx, multi, frontier_of(cur), 0, cnt, cur.prefix, frontier_of(next));
+        ctx->interior += cnt;
+        cnt = children, ++lv, --remaining;
+      }
+      /* keep every shard_count-th subtree */
+      const size_t mine = cnt > shard_index ? (cnt - shard_index + shard_count - 1) / shard_count : 0;
+      if (mine) {
+        alloc_level(ctx, ctx->spare, ctx->capacity);
+        k_gather_shard<<<grid_for(ctx, mine, 256, 8), 256, 0, ctx->stream>>>(frontier_of(ctx->levels[lv]), mine, shard_index,
+                                                                            shard_count, frontier_of(ctx->spare));
+        LAUNCHED();
+        std::swap(ctx->levels[lv], ctx->spare);
+        descend(ctx, lv, mine, remaining, multi);
+      }
+    }
+    timer.end_device();
+    CK(cudaMemcpyAsync(nodes_out, ctx->d_nodes, n_out * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_result + 2, ctx->d_visited, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->interior += ctx->h_result[2];
+    /* every node of plies 1..d-1 written once and read once at 64 B */
+    timer.finish(timing, 2 * 64 * (ctx->interior > n ? ctx->interior - n : 0));
+    return 0;
+  } catch (const CudaFail& f) {
+    return fail(ctx, f);
+  } catch (const std::bad_alloc&) {
+    ctx->error = "out of host memory";
+    return -3;
+  }
+}
+
+} /* namespace */
+
+extern "C" {
+
+int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) {
+  if (!out) return -1;
+  *out = nullptr;
+  pabi_cuda_ctx* ctx = new (std::nothrow) pabi_cuda_ctx;
+  if (!ctx) return -3;
+  try {
+    if (device < 0) CK(cudaGetDevice(&device));
+    CK(cudaSetDevice(device));
+    ctx->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    if (frontier_capacity) ctx->capacity = frontier_capacity < 4096 ? 4096 : frontier_capacity;
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ctx->ev0));
+    CK(cudaEventCreate(&ctx->ev1));
+    const HostTables& h = host_tables();
+    CK(cudaMalloc(&ctx->d_tables, sizeof(SharedTables)));
+    CK(cudaMalloc(&ctx->d_rook, sizeof h.rook_attacks));
+    CK(cudaMalloc(&ctx->d_rays, sizeof h.rays));
+    CK(cudaMemcpy(ctx->d_tables, &h.shared, sizeof(SharedTables), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_rook, h.rook_attacks, sizeof h.rook_attacks, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_rays, h.rays, sizeof h.rays, cudaMemcpyHostToDevice));
+    ctx->dt.image = (const SharedTables*)ctx->d_tables;
+    ctx->dt.g.rook_attacks = ctx->d_rook;
+    ctx->dt.g.rays = ctx->d_rays;
+    CK(cudaMalloc(&ctx->d_result, 4 * sizeof(u64)));
+    CK(cudaMalloc(&ctx->d_visited, sizeof(unsigned long long)));
+    CK(cudaMallocHost(&ctx->h_result, 4 * sizeof(u64)));
+    /* kernels that stage the table image need more than the default 48 KB of dynamic shared memory */
+    CK(cudaFuncSetAttribute(k_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_count_accumulate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_count_accumulate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_in_check, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_make_moves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_emit_moves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_tile<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+    CK(cudaFuncSetAttribute(k_tile<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+    CK(cudaFuncSetAttribute(k_tile<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+    CK(cudaFuncSetAttribute(k_tile<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+  } catch (const CudaFail& f) {
+    std::fprintf(stderr, "pabi_cuda_create: %s\n", ctx->error.c_str());
+    int code = (int)f.code;
+    pabi_cuda_destroy(ctx);
+    return code;
+  }
+  *out = ctx;
+  return 0;
+}
+
+void pabi_cuda_destroy(pabi_cuda_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  auto free_level = [](Level& l) {
+    if (l.rec) cudaFree(l.rec), cudaFree(l.roots), cudaFree(l.counts), cudaFree(l.prefix);
+    l = Level();
+  };
+  for (Level& l : ctx->levels) free_level(l);
+  free_level(ctx->spare);
+  for (Buffer& b : ctx->scratch)
+    if (b.ptr) cudaFree(b.ptr);
+  if (ctx->d_tile_sums) cudaFree(ctx->d_tile_sums);
+  if (ctx->d_result) cudaFree(ctx->d_result);
+  if (ctx->d_visited) cudaFree(ctx->d_visited);
+  if (ctx->h_result) cudaFreeHost(ctx->h_result);
+  if (ctx->d_nodes) cudaFree(ctx->d_nodes);
+  if (ctx->d_tables) cudaFree(ctx->d_tables);
+  if (ctx->d_rook) cudaFree(ctx->d_rook);
+  if (ctx->d_rays) cudaFree(ctx->d_rays);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* pabi_cuda_last_error(pabi_cuda_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+int pabi_cuda_device(const pabi_cuda_ctx* ctx) { return ctx ? ctx->device : -1; }
+
+int pabi_cuda_perft(pabi_cuda_ctx* ctx, const pabi_position_t* root, uint8_t depth, uint64_t* nodes, pabi_timing_t* timing) {
+  if (!ctx || !root || !nodes) return bad_arg(ctx, "null argument");
+  return perft_impl(ctx, root, 1, depth, nodes, false, 0, 0, 1, timing);
+}
+
+int pabi_cuda_perft_batch(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, uint8_t depth, uint64_t* nodes_out,
+                          pabi_timing_t* timing) {
+  if (!ctx || (n && (!roots || !nodes_out))) return bad_arg(ctx, "null argument");
+  if (n == 0) {
+    if (timing) std::memset(timing, 0, sizeof *timing);
+    return 0;
+  }
+  if (n > ctx->capacity) return bad_arg(ctx, "more roots than the frontier capacity");
+  return perft_impl(ctx, roots, n, depth, nodes_out, true, 0, 0, 1, timing);
+}
+
+int pabi_cuda_perft_shard(pabi_cuda_ctx* ctx, const pabi_position_t* root, uint8_t depth, uint32_t split_ply,
+                          uint32_t shard_index, uint32_t shard_count, uint64_t* nodes, pabi_timing_t* timing) {
+  if (!ctx || !root || !nodes) return bad_arg(ctx, "null argument");
+  if (shard_count == 0 || shard_index >= shard_count) return bad_arg(ctx, "shard_index must be < shard_count");
+  return perft_impl(ctx, root, 1, depth, nodes, false, split_ply, shard_index, shard_count, timing);
+}
+
+int pabi_cuda_count_moves_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, size_t n, uint32_t* counts,
+                                pabi_timing_t* timing) {
+  if (!ctx || (n && (!positions || !counts))) return bad_arg(ctx, "null argument");
+  try {
+    CK(cudaSetDevice(ctx->device));
+    CallTimer timer(ctx);
+    if (n == 0) {
+      timer.begin_device(), timer.end_device(), timer.finish(timing, 0);
+      return 0;
+    }
+    upload_roots(ctx, positions, n);
+    Level& l0 = ctx->levels[0];
+    timer.begin_device();
+    k_count<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, l0.rec, l0.cap, 0, n, l0.counts);
+    LAUNCHED();
+    ctx->interior += n;
+    timer.end_device();
+    CK(cudaMemcpyAsync(counts, l0.counts, n * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    timer.finish(timing, 68 * n);
+    return 0;
+  } catch (const CudaFail& f) {
+    return fail(ctx, f);
+  }
+}
+
+int pabi_cuda_in_check_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, size_t n, uint8_t* in_check,
+                             pabi_timing_t* timing) {
+  if (!ctx || (n && (!positions || !in_check))) return bad_arg(ctx, "null argument");
+  try {
+    CK(cudaSetDevice(ctx->device));
+    CallTimer timer(ctx);
+    if (n == 0) {
+      timer.begin_device(), timer.end_device(), timer.finish(timing, 0);
+      return 0;
+    }
+    upload_roots(ctx, positions, n);
+    Level& l0 = ctx->levels[0];
+    u8* d_out = (u8*)ensure(ctx, 1, n);
+    timer.begin_device();
+    k_in_check<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, l0.rec, l0.cap, n, d_out);
+    LAUNCHED();
+    timer.end_device();
+    CK(cudaMemcpyAsync(in_check, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    timer.finish(timing, 65 * n);
+    return 0;
+  } catch (const CudaFail& f) {
+    return fail(ctx, f);
+  }
+}
+
+int pabi_cuda_make_moves_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, const pabi_move_t* moves, size_t n,
+                               pabi_position_t* out, pabi_timing_t* timing) {
+  if (!ctx || (n && (!positions || !moves || !out))) return bad_arg(ctx, "null argument");
+  try {
+    CK(cudaSetDevice(ctx->device));
+    CallTimer timer(ctx);
+    if (n == 0) {
+      timer.begin_device(), timer.end_device(), timer.finish(timing, 0);
+      return 0;
+    }
+    upload_roots(ctx, positions, n);
+    Level& l0 = ctx->levels[0];
+    u16* d_moves = (u16*)ensure(ctx, 1, n * sizeof(u16));
+    u64* d_rec = (u64*)ensure(ctx, 2, n * POS_WORDS * sizeof(u64));
+    PositionImage* d_out = (PositionImage*)ensure(ctx, 3, n * sizeof(PositionImage));
+    CK(cudaMemcpyAsync(d_moves, moves, n * sizeof(u16), cudaMemcpyHostToDevice, ctx->stream));
+    timer.begin_device();
+    k_make_moves<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, l0.rec, l0.cap, n, d_moves,
+                                                                                            d_rec, n);
+    LAUNCHED();
+    k_unpack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(d_rec, n, n, d_out);
+    LAUNCHED();
+    timer.end_device();
+    CK(cudaMemcpyAsync(out, d_out, n * sizeof(PositionImage), cudaMemcpyDeviceToHost, ctx->stream));
+    timer.finish(timing, 130 * n);
+    return 0;
+  } catch (const CudaFail& f) {
+    return fail(ctx, f);
+  }
+}
+
+int pabi_cuda_generate_moves_device(pabi_cuda_ctx* ctx, const uint64_t* device_records, size_t stride, size_t n,
+                                    uint32_t* device_offsets, pabi_move_t* device_moves, size_t moves_cap,
+                                    uint64_t* total_moves, pabi_timing_t* timing) {
+  if (!ctx || !device_records || !device_offsets || !total_moves) return bad_arg(ctx, "null argument");
+  try {
+    CK(cudaSetDevice(ctx->device));
+    CallTimer timer(ctx);
+    u32* counts = (u32*)ensure(ctx, 4, (n + 1) * sizeof(u32));
+    u64* prefix = (u64*)ensure(ctx, 5, (n + 2) * sizeof(u64));
+    timer.begin_device();
+    if (n) {
+      count_and_scan(ctx, device_records, stride, 0, n, counts, prefix);
+      k_emit_moves<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(
+          ctx->dt, device_records, stride, n, prefix, device_moves, device_moves ? moves_cap : 0, device_offsets);
+      LAUNCHED();
+      CK(cudaMemcpyAsync(ctx->h_result, prefix + n, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      CK(cudaMemsetAsync(device_offsets, 0, sizeof(u32), ctx->stream));
+      ctx->h_result[0] = 0;
+    }
+    timer.end_device();
+    timer.finish(timing, 0);
+    *total_moves = ctx->h_result[0];
+    if (timing) timing->algorithmic_bytes = 64 * n + 4 * (n + 1) + 2 * *total_moves;
+    return *total_moves > moves_cap && device_moves ? -2 : 0;
+  } catch (const CudaFail& f) {
+    return fail(ctx, f);
+  }
+}
+
+int pabi_cuda_pack_records(pabi_cuda_ctx* ctx, const pabi_position_t* positions, size_t n, uint64_t* device_records,
+                           size_t stride) {
+  if (!ctx || (n && (!positions || !device_records)) || stride < n) return bad_arg(ctx, "bad argument");
+  try {
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) return 0;
+    void* staging = ensure(ctx, 0, n * sizeof(pabi_position_t));
+    CK(cudaMemcpyAsync(staging, positions, n * sizeof(pabi_position_t), cudaMemcpyHostToDevice, ctx->stream));
+    k_pack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>((const PositionImage*)staging, n, device_records, stride, 0, nullptr);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  } catch (const CudaFail& f) {
+    return fail(ctx, f);
+  }
+}
+
+int pabi_cuda_generate_moves_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, size_t n, uint32_t* offsets,
+                                   pabi_move_t* moves, size_t moves_cap, pabi_timing_t* timing) {
+  if (!ctx || !offsets || (n && !positions) || (moves_cap && !moves)) return bad_arg(ctx, "null argument");
+  try {
+    CK(cudaSetDevice(ctx->device));
+    CallTimer timer(ctx);
+    if (n == 0) {
+      offsets[0] = 0;
+      timer.begin_device(), timer.end_device(), timer.finish(timing, 0);
+      return 0;
+    }
+    if (n >= 0xFFFFFFFFull / 256) return bad_arg(ctx, "batch too large for 32-bit CSR offsets");
+    upload_roots(ctx, positions, n);
+    Level& l0 = ctx->levels[0];
+    u32* d_offsets = (u32*)ensure(ctx, 1, (n + 1) * sizeof(u32));
+    u16* d_moves = moves_cap ? (u16*)ensure(ctx, 2, moves_cap * sizeof(u16)) : nullptr;
+    alloc_level(ctx, l0, n); /* counts/prefix of level 0 are the sizing arrays */
+    timer.begin_device();
+    count_and_scan(ctx, l0.rec, l0.cap, 0, n, l0.counts, l0.prefix);
+    k_emit_moves<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, l0.rec, l0.cap, n, l0.prefix,
+                                                                                            d_moves, moves_cap, d_offsets);
+    LAUNCHED();
+    timer.end_device();
+    CK(cudaMemcpyAsync(offsets, d_offsets, (n + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t total = offsets[n];
+    if (total <= moves_cap && total)
+      CK(cudaMemcpyAsync(moves, d_moves, total * sizeof(u16), cudaMemcpyDeviceToHost, ctx->stream));
+    timer.finish(timing, 64 * n + 4 * (n + 1) + 2 * total);
+    if (total > moves_cap) {
+      ctx->error = "moves_cap too small; offsets[n] holds the required size";
+      return -2;
+    }
+    return 0;
+  } catch (const CudaFail& f) {
+    return fail(ctx, f);
+  }
+}
+
+int pabi_cuda_expand_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, size_t n, uint32_t* offsets,
+                           pabi_position_t* children, size_t children_cap, pabi_timing_t* timing) {
+  if (!ctx || !offsets || (n && !positions)) return bad_arg(ctx, "null argument");
+  try {
+    CK(cudaSetDevice(ctx->device));
+    CallTimer timer(ctx);
+    if (n == 0) {
+      offsets[0] = 0;
+      timer.begin_device(), timer.end_device(), timer.finish(timing, 0);
+      return 0;
+    }
+    if (n >= 0xFFFFFFFFull / 256) return bad_arg(ctx, "batch too large for 32-bit CSR offsets");
+    upload_roots(ctx, positions, n);
+    Level& l0 = ctx->levels[0];
+    u32* d_offsets = (u32*)ensure(ctx, 1, (n + 1) * sizeof(u32));
+    timer.begin_device();
+    count_and_scan(ctx, l0.rec, l0.cap, 0, n, l0.counts, l0.prefix);
+    /* offsets = low 32 bits of the prefix: reuse k_emit_moves with no move buffer */
+    k_emit_moves<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, l0.rec, l0.cap, n, l0.prefix,
+                                                                                            nullptr, 0, d_offsets);
+    LAUNCHED();
+    CK(cudaMemcpyAsync(offsets, d_offsets, (n + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t total = offsets[n];
+    if (children && total > children_cap) {
+      timer.end_device();
+      timer.finish(timing, 0);
+      ctx->error = "children_cap too small; offsets[n] holds the required size";
+      return -2;
+    }
+    if (children && total) {
+      if (total > ctx->capacity) return bad_arg(ctx, "children exceed the frontier capacity");
+      Level& l1 = ctx->levels[1];
+      alloc_level(ctx, l1, ctx->capacity);
+      launch_tile<false>(ctx, true, frontier_of(l0), 0, n, l0.prefix, frontier_of(l1));
+      PositionImage* d_out = (PositionImage*)ensure(ctx, 3, total * sizeof(PositionImage));
+      k_unpack<<<grid_for(ctx, total, 256, 8), 256, 0, ctx->stream>>>(l1.rec, l1.cap, total, d_out);
+      LAUNCHED();
+      timer.end_device();
+      CK(cudaMemcpyAsync(children, d_out, total * sizeof(PositionImage), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      timer.end_device();
+    }
+    timer.finish(timing, 64 * n + 64 * total);
+    return 0;
+  } catch (const CudaFail& f) {
+    return fail(ctx, f);
+  }
+}
+
+int pabi_cuda_perft_divide(pabi_cuda_ctx* ctx, const pabi_position_t* root, uint8_t depth, pabi_move_t moves_out[PABI_MAX_MOVES],
+                           uint64_t nodes_out[PABI_MAX_MOVES], uint32_t* n_moves, pabi_timing_t* timing) {
+  if (!ctx || !root || !moves_out || !nodes_out || !n_moves) return bad_arg(ctx, "null argument");
+  if (depth == 0) return bad_arg(ctx, "divide needs depth >= 1");
+  uint32_t offsets[2];
+  int rc = pabi_cuda_generate_moves_batch(ctx, root, 1, offsets, moves_out, PABI_MAX_MOVES, nullptr);
+  if (rc) return rc;
+  *n_moves = offsets[1];
+  std::vector<pabi_position_t> children(*n_moves ? *n_moves : 1);
+  rc = pabi_cuda_expand_batch(ctx, root, 1, offsets, children.data(), children.size(), nullptr);
+  if (rc) return rc;
+  if (*n_moves == 0) {
+    if (timing) std::memset(timing, 0, sizeof *timing);
+    return 0;
+  }
+  return pabi_cuda_perft_batch(ctx, children.data(), *n_moves, (uint8_t)(depth - 1), nodes_out, timing);
+}
+
+} /* extern "C" */

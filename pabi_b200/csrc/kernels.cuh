@@ -1,0 +1,423 @@
+/*
+ * kernels.cuh -- sm_100a kernels of the perft / move-generation path.
+ *
+ * K0  stage_tables        (device fn) 50 KB table image -> shared memory, once per block
+ * K1  k_expand            one breadth-first ply: parents (SoA, HBM) -> children (SoA, HBM)
+ * K2  k_leaf2             last two plies fused: parents -> children in shared memory ->
+ *                         count-only move generation per child, nothing written to HBM
+ *     k_count             generate_moves().len() per record (perft depth 1, sizing pass of K1/K3)
+ * K3  k_emit_moves        ordered u16 move lists at CSR offsets
+ * K4  k_scan_*            exclusive prefix sum u32 -> u64 (reduce / spine / down-sweep)
+ * K5  per-root accumulation, fused into k_leaf2 / k_count_accumulate
+ *
+ * All of them are HBM/issue-bound integer kernels; no tensor cores (nothing here
+ * is a contraction).  Position arithmetic is chess.cuh.
+ */
+#pragma once
+#include <cuda_runtime.h>
+
+#include "chess.cuh"
+
+namespace pabi {
+
+/* ---- shared-memory table staging (K0) ----------------------------------- */
+__device__ __forceinline__ void stage_tables(SharedTables* dst, const SharedTables* __restrict__ src) {
+  static_assert(sizeof(SharedTables) % 16 == 0, "table image must be uint4-copyable");
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  for (u32 i = threadIdx.x; i < sizeof(SharedTables) / 16; i += blockDim.x) d[i] = __ldg(s + i);
+  __syncthreads();
+}
+
+struct DeviceTables {
+  const SharedTables* image; /* global copy of the shared-memory image */
+  GlobalTables g;
+};
+
+/* SoA view of a frontier: word w of record i at rec[w * stride + i]. */
+struct Frontier {
+  u64* rec;
+  u32* roots; /* root index of each record (perft_batch), may be null when single-root */
+  size_t stride;
+};
+
+/* ---- block-wide helpers -------------------------------------------------- */
+template <int THREADS>
+__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* warp_sums /* [THREADS/32 + 1] */, u32& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u32 inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    u32 o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    constexpr int NW = THREADS / 32;
+    u32 w = lane < NW ? warp_sums[lane] : 0;
+    u32 winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      u32 o = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+      if (lane >= d) winc += o;
+    }
+    if (lane < NW) warp_sums[lane] = winc - w;
+    if (lane == NW - 1) warp_sums[NW] = winc;
+  }
+  __syncthreads();
+  total = warp_sums[THREADS / 32];
+  const u32 r = warp_sums[warp] + inc - v;
+  __syncthreads(); /* warp_sums may be reused by the caller's next scan */
+  return r;
+}
+
+__device__ __forceinline__ u64 warp_sum_u64(u64 v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
+  return v;
+}
+
+/* One atomicAdd per block on *dst. */
+template <int THREADS>
+__device__ __forceinline__ void block_add_u64(u64 v, u64* scratch /* [THREADS/32] */, unsigned long long* dst) {
+  v = warp_sum_u64(v);
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    u64 w = threadIdx.x < THREADS / 32 ? scratch[threadIdx.x] : 0;
+    w = warp_sum_u64(w);
+    if (threadIdx.x == 0 && w) atomicAdd(dst, (unsigned long long)w);
+  }
+}
+
+/* ---- simple thread-per-record kernels ------------------------------------ */
+constexpr int FLAT_THREADS = 256;
+
+/* counts[i] = generate_moves().len() of record first + i */
+__global__ void __launch_bounds__(FLAT_THREADS)
+k_count(DeviceTables dt, const u64* __restrict__ rec, size_t stride, size_t first, size_t n, u32* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SharedTables* st = reinterpret_cast<SharedTables*>(smem);
+  stage_tables(st, dt.image);
+  const Tables tb{st, dt.g};
+  for (size_t i = (size_t)blockIdx.x * FLAT_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * FLAT_THREADS)
+    counts[i] = count_moves(load_pos(rec, stride, first + i), tb);
+}
+
+/* perft with one ply left: nodes[root] += generate_moves().len() (position.rs:914-916) */
+template <bool MULTI_ROOT>
+__global__ void __launch_bounds__(FLAT_THREADS)
+k_count_accumulate(DeviceTables dt, Frontier f, size_t n, unsigned long long* __restrict__ nodes) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SharedTables* st = reinterpret_cast<SharedTables*>(smem);
+  __shared__ u64 red[FLAT_THREADS / 32];
+  stage_tables(st, dt.image);
+  const Tables tb{st, dt.g};
+  u64 acc = 0;
+  for (size_t i = (size_t)blockIdx.x * FLAT_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * FLAT_THREADS) {
+    const u32 c = count_moves(load_pos(f.rec, f.stride, i), tb);
+    if (MULTI_ROOT) {
+      if (c) atomicAdd(nodes + f.roots[i], (unsigned long long)c);
+    } else {
+      acc += c;
+    }
+  }
+  if (!MULTI_ROOT) block_add_u64<FLAT_THREADS>(acc, red, nodes);
+}
+
+/* in_check (position.rs:735-746) */
+__global__ void __launch_bounds__(FLAT_THREADS)
+k_in_check(DeviceTables dt, const u64* __restrict__ rec, size_t stride, size_t n, u8* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SharedTables* st = reinterpret_cast<SharedTables*>(smem);
+  stage_tables(st, dt.image);
+  const Tables tb{st, dt.g};
+  for (size_t i = (size_t)blockIdx.x * FLAT_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * FLAT_THREADS) {
+    Analysis a;
+    analyze(load_pos(rec, stride, i), tb, a);
+    out[i] = a.checkers != 0;
+  }
+}
+
+/* out[i] = rec[i] after moves[i] (position.rs:414-433) */
+__global__ void __launch_bounds__(FLAT_THREADS)
+k_make_moves(DeviceTables dt, const u64* __restrict__ rec, size_t stride, size_t n, const u16* __restrict__ moves,
+             u64* __restrict__ out, size_t out_stride) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SharedTables* st = reinterpret_cast<SharedTables*>(smem);
+  stage_tables(st, dt.image);
+  const Tables tb{st, dt.g};
+  for (size_t i = (size_t)blockIdx.x * FLAT_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * FLAT_THREADS) {
+    Pos p = load_pos(rec, stride, i);
+    make_move(p, tb, moves[i]);
+    store_pos(out, out_stride, i, p);
+  }
+}
+
+/* K3: ordered move lists.  moves[prefix[i] - prefix[0] ...] in generate_moves order. */
+__global__ void __launch_bounds__(FLAT_THREADS)
+k_emit_moves(DeviceTables dt, const u64* __restrict__ rec, size_t stride, size_t n, const u64* __restrict__ prefix,
+             u16* __restrict__ moves, size_t moves_cap, u32* __restrict__ offsets) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SharedTables* st = reinterpret_cast<SharedTables*>(smem);
+  stage_tables(st, dt.image);
+  const Tables tb{st, dt.g};
+  for (size_t i = (size_t)blockIdx.x * FLAT_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * FLAT_THREADS) {
+    const u64 base = prefix[i];
+    if (offsets) {
+      offsets[i] = (u32)base;
+      if (i + 1 == n) offsets[n] = (u32)prefix[n];
+    }
+    if (prefix[i + 1] > moves_cap) continue;
+    u16* dst = moves + base;
+    generate_moves(load_pos(rec, stride, i), tb, [&](int from, int to, int promo) { *dst++ = pack_move(from, to, promo); });
+  }
+}
+
+/* ---- AoS (pabi_position_t, 112 B) <-> SoA record conversion -------------- */
+struct PositionImage { /* == pabi_position_t */
+  u64 white[6], black[6], hash;
+  u16 fullmove;
+  u8 castling, stm, halfmove, ep, pad[2];
+};
+static_assert(sizeof(PositionImage) == 112, "pabi_position_t image");
+
+__global__ void k_pack(const PositionImage* __restrict__ in, size_t n, u64* __restrict__ rec, size_t stride, size_t first,
+                       u32* __restrict__ roots) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const PositionImage& q = in[i];
+    Pos p;
+    p.white = q.white[0] | q.white[1] | q.white[2] | q.white[3] | q.white[4] | q.white[5];
+    p.kings = q.white[0] | q.black[0];
+    p.queens = q.white[1] | q.black[1];
+    p.rooks = q.white[2] | q.black[2];
+    p.bishops = q.white[3] | q.black[3];
+    p.knights = q.white[4] | q.black[4];
+    p.pawns = q.white[5] | q.black[5];
+    p.meta = make_meta(q.castling & 15, q.ep > 63 ? NO_SQUARE : q.ep, q.stm & 1, q.halfmove, q.fullmove);
+    store_pos(rec, stride, first + i, p);
+    if (roots) roots[first + i] = (u32)i;
+  }
+}
+
+__global__ void k_unpack(const u64* __restrict__ rec, size_t stride, size_t n, PositionImage* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const Pos p = load_pos(rec, stride, i);
+    PositionImage q;
+    const u64 w = p.white;
+    q.white[0] = p.kings & w, q.black[0] = p.kings & ~w;
+    q.white[1] = p.queens & w, q.black[1] = p.queens & ~w;
+    q.white[2] = p.rooks & w, q.black[2] = p.rooks & ~w;
+    q.white[3] = p.bishops & w, q.black[3] = p.bishops & ~w;
+    q.white[4] = p.knights & w, q.black[4] = p.knights & ~w;
+    q.white[5] = p.pawns & w, q.black[5] = p.pawns & ~w;
+    q.hash = 0;
+    q.fullmove = (u16)meta_fullmove(p.meta);
+    q.castling = (u8)meta_castling(p.meta);
+    q.stm = (u8)meta_stm(p.meta);
+    q.halfmove = (u8)meta_halfmove(p.meta);
+    q.ep = (u8)meta_ep(p.meta);
+    q.pad[0] = q.pad[1] = 0;
+    out[i] = q;
+  }
+}
+
+/* every shard_count-th record starting at shard_index (root-subtree sharding) */
+__global__ void k_gather_shard(Frontier in, size_t n_out, u32 shard_index, u32 shard_count, Frontier out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t src = (size_t)shard_index + i * shard_count;
+    store_pos(out.rec, out.stride, i, load_pos(in.rec, in.stride, src));
+    if (out.roots) out.roots[i] = in.roots ? in.roots[src] : 0;
+  }
+}
+
+/* ---- K4: exclusive scan u32 -> u64, prefix[0..n] (prefix[n] = total) ------ */
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_reduce(const u32* __restrict__ in, size_t n, u64* __restrict__ tile_sums) {
+  __shared__ u64 red[SCAN_THREADS / 32];
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE;
+  u64 s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    const size_t i = base + (size_t)k * SCAN_THREADS + threadIdx.x;
+    if (i < n) s += in[i];
+  }
+  s = warp_sum_u64(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    u64 w = threadIdx.x < SCAN_THREADS / 32 ? red[threadIdx.x] : 0;
+    w = warp_sum_u64(w);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = w;
+  }
+}
+
+/* single block: exclusive scan of the tile sums in place */
+__global__ void __launch_bounds__(1024) k_scan_spine(u64* __restrict__ tile_sums, size_t n_tiles) {
+  __shared__ u64 warp_tot[32];
+  __shared__ u64 carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (size_t base = 0; base < n_tiles; base += 1024) {
+    const size_t i = base + threadIdx.x;
+    const u64 v = i < n_tiles ? tile_sums[i] : 0;
+    u64 inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      u64 o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      u64 w = warp_tot[lane], winc = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        u64 o = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+        if (lane >= d) winc += o;
+      }
+      warp_tot[lane] = winc - w;
+    }
+    __syncthreads();
+    const u64 c = carry;
+    if (i < n_tiles) tile_sums[i] = c + warp_tot[warp] + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = c + warp_tot[warp] + inc;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_down(const u32* __restrict__ in, size_t n, const u64* __restrict__ tile_sums, u64* __restrict__ prefix) {
+  __shared__ u32 warp_sums[SCAN_THREADS / 32 + 1];
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  u32 v[SCAN_ITEMS];
+  u32 s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    v[k] = base + k < n ? in[base + k] : 0;
+    s += v[k];
+  }
+  u32 total;
+  u32 off = block_exclusive_scan<SCAN_THREADS>(s, warp_sums, total);
+  u64 run = tile_sums[blockIdx.x] + off;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    if (base + k < n) prefix[base + k] = run;
+    run += v[k];
+    if (base + k + 1 == n) prefix[n] = run;
+  }
+}
+
+/* Largest end in [start, n] with prefix[end] - prefix[start] <= capacity; result {end, children}. */
+__global__ void k_chunk_end(const u64* __restrict__ prefix, size_t start, size_t n, u64 capacity, u64* __restrict__ result) {
+  if (threadIdx.x || blockIdx.x) return;
+  const u64 base = prefix[start];
+  size_t lo = start, hi = n; /* invariant: prefix[lo] - base <= capacity */
+  while (lo < hi) {
+    const size_t mid = lo + (hi - lo + 1) / 2;
+    if (prefix[mid] - base <= capacity) lo = mid; else hi = mid - 1;
+  }
+  result[0] = lo;
+  result[1] = prefix[lo] - base;
+}
+
+/* ---- K1 / K2: tile kernels ------------------------------------------------
+ * A block takes TILE_THREADS consecutive parents at a time:
+ *   A0  every thread counts the moves of its parent; block exclusive scan
+ *   A   every thread generates its parent's moves (reference order) into the
+ *       shared pool at its scanned offset, as (parent << 16 | move)
+ *   B   every thread takes children from the pool: parent record from shared
+ *       memory, make_move in registers, then
+ *         K1: store the child record (coalesced SoA) at its global offset
+ *         K2: count the child's moves and accumulate -- the children are never
+ *             written to HBM
+ * If a tile has more children than the pool holds, A/B repeat over windows. */
+constexpr int TILE_THREADS = 256;
+constexpr int POOL_CAP = 8192;
+
+struct TileShared {
+  SharedTables tables;
+  u64 parents[POS_WORDS][TILE_THREADS];
+  u32 pool[POOL_CAP];
+  u32 parent_nodes[TILE_THREADS]; /* K2, multi-root: nodes below each parent */
+  u32 warp_sums[TILE_THREADS / 32 + 1];
+  u64 red[TILE_THREADS / 32];
+};
+
+template <bool LEAF, bool MULTI_ROOT>
+__global__ void __launch_bounds__(TILE_THREADS, 2)
+k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restrict__ prefix, Frontier out,
+       unsigned long long* __restrict__ nodes, unsigned long long* __restrict__ visited) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  TileShared& sh = *reinterpret_cast<TileShared*>(smem);
+  stage_tables(&sh.tables, dt.image);
+  const Tables tb{&sh.tables, dt.g};
+  const int tid = threadIdx.x;
+  u64 acc = 0;
+  const size_t n_tiles = (n + TILE_THREADS - 1) / TILE_THREADS;
+
+  for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const size_t i = tile * TILE_THREADS + tid;
+    const bool valid = i < n;
+    Pos p;
+    u32 cnt = 0;
+    if (valid) {
+      p = load_pos(in.rec, in.stride, first + i);
+      sh.parents[0][tid] = p.white, sh.parents[1][tid] = p.pawns, sh.parents[2][tid] = p.knights;
+      sh.parents[3][tid] = p.bishops, sh.parents[4][tid] = p.rooks, sh.parents[5][tid] = p.queens;
+      sh.parents[6][tid] = p.kings, sh.parents[7][tid] = p.meta;
+      cnt = count_moves(p, tb);
+    }
+    if (LEAF && MULTI_ROOT) sh.parent_nodes[tid] = 0;
+    u32 total;
+    const u32 off = block_exclusive_scan<TILE_THREADS>(cnt, sh.warp_sums, total);
+    if (LEAF && tid == 0 && total) atomicAdd(visited, (unsigned long long)total); /* statistics: positions at the last ply but one */
+    /* global index of this tile's first child (K1); prefix comes from the same count */
+    const u64 child_base = LEAF ? 0 : prefix[first + tile * TILE_THREADS] - prefix[first];
+
+    for (u32 w = 0; w < total; w += POOL_CAP) {
+      if (cnt && off < w + POOL_CAP && off + cnt > w) {
+        u32 j = off;
+        generate_moves(p, tb, [&](int from, int to, int promo) {
+          const u32 slot = j++ - w; /* wraps to a huge value below the window */
+          if (slot < (u32)POOL_CAP) sh.pool[slot] = ((u32)tid << 16) | pack_move(from, to, promo);
+        });
+      }
+      __syncthreads();
+      const u32 end = min(total - w, (u32)POOL_CAP);
+      for (u32 c = tid; c < end; c += TILE_THREADS) {
+        const u32 e = sh.pool[c];
+        const int parent = e >> 16;
+        Pos q;
+        q.white = sh.parents[0][parent], q.pawns = sh.parents[1][parent], q.knights = sh.parents[2][parent];
+        q.bishops = sh.parents[3][parent], q.rooks = sh.parents[4][parent], q.queens = sh.parents[5][parent];
+        q.kings = sh.parents[6][parent], q.meta = sh.parents[7][parent];
+        make_move(q, tb, (u16)(e & 0xFFFF));
+        if (LEAF) {
+          const u32 k = count_moves(q, tb);
+          if (MULTI_ROOT) atomicAdd(&sh.parent_nodes[parent], k);
+          else acc += k;
+        } else {
+          const size_t o = (size_t)(child_base + w + c);
+          store_pos(out.rec, out.stride, o, q);
+          if (MULTI_ROOT) out.roots[o] = in.roots[first + tile * TILE_THREADS + parent];
+        }
+      }
+      __syncthreads();
+    }
+    if (LEAF && MULTI_ROOT) {
+      if (valid && sh.parent_nodes[tid]) atomicAdd(nodes + in.roots[first + i], (unsigned long long)sh.parent_nodes[tid]);
+      __syncthreads();
+    }
+  }
+  if (LEAF && !MULTI_ROOT) block_add_u64<TILE_THREADS>(acc, sh.red, nodes);
+}
+
+} /* namespace pabi */

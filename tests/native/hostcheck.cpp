@@ -1,0 +1,134 @@
+/*
+ * hostcheck.cpp -- TEST INFRASTRUCTURE.  Compiles the product's device
+ * arithmetic (pabi_b200/csrc/chess.cuh, every function of which is
+ * __host__ __device__) for the host CPU, so the CPU test-suite can compare the
+ * exact logic the kernels inline with the oracle on millions of positions
+ * without a GPU.  Never linked into libpabi_b200.so.
+ */
+#include "../../pabi_b200/csrc/record.h"
+#include "../../pabi_b200/csrc/tables.h"
+
+using namespace pabi;
+
+static Tables host_tb() {
+  const HostTables& h = host_tables();
+  Tables t;
+  t.s = &h.shared;
+  t.g.rook_attacks = h.rook_attacks;
+  t.g.rays = h.rays;
+  return t;
+}
+
+extern "C" {
+
+uint32_t hostcheck_count_moves(const pabi_position_t* p) { return count_moves(pack_record(*p), host_tb()); }
+
+uint32_t hostcheck_generate_moves(const pabi_position_t* p, uint16_t* out) {
+  uint32_t k = 0;
+  return generate_moves(pack_record(*p), host_tb(), [&](int f, int t, int pr) { out[k++] = pack_move(f, t, pr); });
+}
+
+void hostcheck_make_move(pabi_position_t* p, uint16_t mv) {
+  Pos r = pack_record(*p);
+  make_move(r, host_tb(), mv);
+  *p = unpack_record(r, p->hash);
+}
+
+int hostcheck_in_check(const pabi_position_t* p) {
+  Analysis a;
+  analyze(pack_record(*p), host_tb(), a);
+  return a.checkers != 0;
+}
+
+void hostcheck_analysis(const pabi_position_t* p, uint64_t out[5]) {
+  Analysis a;
+  analyze(pack_record(*p), host_tb(), a);
+  out[0] = a.attacks, out[1] = a.checkers, out[2] = a.pins, out[3] = a.safe_king, out[4] = a.block;
+}
+
+static uint64_t perft_rec(const Pos& p, const Tables& tb, int depth) {
+  if (depth == 0) return 1;
+  if (depth == 1) return count_moves(p, tb);
+  uint16_t moves[256];
+  uint32_t k = 0;
+  generate_moves(p, tb, [&](int f, int t, int pr) { moves[k++] = pack_move(f, t, pr); });
+  uint64_t n = 0;
+  for (uint32_t i = 0; i < k; i++) {
+    Pos c = p;
+    make_move(c, tb, moves[i]);
+    n += perft_rec(c, tb, depth - 1);
+  }
+  return n;
+}
+uint64_t hostcheck_perft(const pabi_position_t* p, int depth) { return perft_rec(pack_record(*p), host_tb(), depth); }
+
+/* Walks the perft tree of `root` to `depth` comparing, at every node, the
+ * product logic with callbacks into the oracle (passed as function pointers so
+ * this file does not link the oracle).  Returns the number of mismatching nodes;
+ * first_bad receives the first offending position. */
+typedef uint32_t (*oracle_gen_fn)(const pabi_position_t*, uint16_t*);
+typedef void (*oracle_make_fn)(pabi_position_t*, uint16_t);
+
+static uint64_t walk_compare(const pabi_position_t& p, int depth, oracle_gen_fn gen, oracle_make_fn mk,
+                             pabi_position_t* first_bad, uint64_t* visited) {
+  uint16_t want[256], got[256];
+  ++*visited;
+  const uint32_t nw = gen(&p, want);
+  const Tables tb = host_tb();
+  const Pos r = pack_record(p);
+  uint32_t k = 0;
+  const uint32_t ng = generate_moves(r, tb, [&](int f, int t, int pr) { got[k++] = pack_move(f, t, pr); });
+  uint64_t bad = 0;
+  if (ng != nw || count_moves(r, tb) != nw) bad = 1;
+  for (uint32_t i = 0; i < nw && !bad; i++)
+    if (want[i] != got[i]) bad = 1;
+  if (bad) {
+    if (first_bad) *first_bad = p;
+    return 1;
+  }
+  if (depth == 0) return 0;
+  for (uint32_t i = 0; i < nw; i++) {
+    pabi_position_t a = p, b = p;
+    mk(&a, want[i]);
+    Pos c = r;
+    make_move(c, tb, want[i]);
+    b = unpack_record(c, a.hash);
+    if (__builtin_memcmp(&a, &b, sizeof a) != 0) {
+      if (first_bad) *first_bad = p;
+      return bad + 1;
+    }
+    bad += walk_compare(a, depth - 1, gen, mk, first_bad, visited);
+    if (bad) return bad;
+  }
+  return bad;
+}
+
+uint64_t hostcheck_walk_compare(const pabi_position_t* root, int depth, oracle_gen_fn gen, oracle_make_fn mk,
+                                pabi_position_t* first_bad, uint64_t* visited) {
+  uint64_t v = 0;
+  uint64_t bad = walk_compare(*root, depth, gen, mk, first_bad, &v);
+  if (visited) *visited = v;
+  return bad;
+}
+
+/* table access for tests/test_tables*.py */
+const uint64_t* hostcheck_table(const char* name, size_t* count) {
+  const HostTables& h = host_tables();
+  struct { const char* n; const uint64_t* p; size_t c; } T[] = {
+      {"knight", h.shared.knight, 64}, {"king", h.shared.king, 64},
+      {"bishop_attacks", h.shared.bishop_attacks, BISHOP_TABLE_SIZE},
+      {"rook_attacks", h.rook_attacks, ROOK_TABLE_SIZE}, {"rays", h.rays, 4096},
+      {"diag", h.shared.diag, 64}, {"anti", h.shared.anti, 64}};
+  for (auto& e : T)
+    if (!__builtin_strcmp(e.n, name)) { *count = e.c; return e.p; }
+  return nullptr;
+}
+uint64_t hostcheck_bishop(int sq, uint64_t occ) { return host_tb().bishop(sq, occ); }
+uint64_t hostcheck_rook(int sq, uint64_t occ) { return host_tb().rook(sq, occ); }
+void hostcheck_slider_entry(int rook, int sq, uint64_t* mask, uint32_t* offset, uint32_t* bits) {
+  const SharedTables& s = host_tables().shared;
+  *mask = rook ? s.rook[sq].mask : s.bishop[sq].mask;
+  uint32_t os = rook ? s.rook_os[sq] : s.bishop_os[sq];
+  *offset = os & 0xFFFFFF, *bits = 32 - (os >> 24);
+}
+}

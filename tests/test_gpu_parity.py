@@ -1,0 +1,197 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI
+(include/pabi_cuda.h via pabi_b200), against the CPU oracle and the reference's
+golden vectors (tests/golden/).  Integer work: everything is compared bit-exact.
+
+Run on the B200 box with `python -m pytest tests -m gpu`.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+KIWIPETE = "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1"
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import pabi_b200
+    return pabi_b200
+
+
+@pytest.fixture(scope="module")
+def engine(pb):
+    e = pb.Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def small_engine(pb):
+    """A context whose frontier buffers hold only 20 000 records: forces the chunked path."""
+    e = pb.Engine(0, frontier_capacity=20000)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def playout_positions():
+    """Seeded random-playout positions (SURVEY.md 8d, config #5 recipe), ~30k."""
+    chunks = []
+    start = oracle.starting()
+    for g in range(400):
+        chunks.append(oracle.random_playout(start, 0x5EED0000 + g, 200))
+    return np.concatenate(chunks)
+
+
+def fen_pos(pb, fen):
+    return pb.Position.starting() if fen == "startpos" else pb.Position.try_from(fen)
+
+
+# ---- perft: the reference's known answers (tests/chess.rs:622-818, benches/chess.rs:52-86) ----
+
+def test_reference_perft_vectors(pb, engine, vectors):
+    checked = 0
+    for case in vectors["perft"] + vectors["bench_perft"]:
+        if case["nodes"] > 2_000_000_000:
+            continue
+        assert engine.perft(fen_pos(pb, case["fen"]), case["depth"]) == case["nodes"], case
+        checked += 1
+    assert checked >= 70
+
+
+def test_startpos_perft_7(pb, engine):
+    assert engine.perft(pb.Position.starting(), 7) == 3_195_901_860
+
+
+def test_reference_deep_vector(pb, engine, vectors):
+    """tests/chess.rs:813-818: depth 7 -> 14 794 751 816."""
+    deep = [c for c in vectors["perft"] if c["nodes"] > 2_000_000_000]
+    assert deep
+    for case in deep:
+        assert engine.perft(fen_pos(pb, case["fen"]), case["depth"]) == case["nodes"], case
+
+
+def test_perft_depth_0_1_2(pb, engine):
+    p = pb.Position.from_fen(KIWIPETE)
+    assert [engine.perft(p, d) for d in range(4)] == [1, 48, 2039, 97862]
+    # no legal moves: checkmate and stalemate
+    mate = pb.Position.from_fen("R5k1/5ppp/8/8/8/8/8/6K1 b - - 0 1")
+    stale = pb.Position.from_fen("7k/5Q2/6K1/8/8/8/8/8 b - - 0 1")
+    for p in (mate, stale):
+        assert [engine.perft(p, d) for d in range(4)] == [1, 0, 0, 0]
+
+
+def test_chunked_search_gives_the_same_counts(pb, small_engine, vectors):
+    for case in vectors["perft"]:
+        if 100_000 < case["nodes"] < 200_000_000:
+            assert small_engine.perft(fen_pos(pb, case["fen"]), case["depth"]) == case["nodes"], case
+
+
+def test_perft_batch_matches_oracle_per_root(engine, playout_positions):
+    batch = playout_positions[::37][:600]
+    for depth in (1, 2, 3):
+        got = engine.perft_batch(batch, depth)
+        want = [oracle.perft(oracle.Position.from_buffer_copy(batch[i].tobytes()), depth) for i in range(len(batch))]
+        assert got.tolist() == want, depth
+
+
+def test_perft_batch_chunked(small_engine, playout_positions):
+    batch = playout_positions[::53][:300]
+    got = small_engine.perft_batch(batch, 4)
+    want = [oracle.perft(oracle.Position.from_buffer_copy(batch[i].tobytes()), 4) for i in range(len(batch))]
+    assert got.tolist() == want
+
+
+def test_shards_sum_to_the_whole(pb, engine):
+    p = pb.Position.from_fen(KIWIPETE)
+    for depth, split in ((4, 1), (4, 2), (5, 2), (3, 5), (1, 2)):
+        whole = engine.perft(p, depth)
+        for count in (1, 2, 3, 8):
+            assert sum(engine.perft_shard(p, depth, split, i, count) for i in range(count)) == whole
+
+
+def test_divide(pb, engine):
+    p = pb.Position.from_fen(KIWIPETE)
+    op = oracle.parse(KIWIPETE)
+    got = engine.divide(p, 3)
+    want = []
+    for m in oracle.generate_moves(op):
+        c = oracle.copy(op)
+        oracle.make_move(c, m)
+        want.append((m, oracle.perft(c, 2)))
+    assert [(m.raw, n) for m, n in got] == want
+    assert sum(n for _, n in got) == 97862
+
+
+# ---- move lists: golden vectors (tests/chess.rs:219-472) and order vs the oracle ----
+
+def test_reference_move_list_vectors(pb, engine, vectors):
+    for case in vectors["move_lists"]:
+        p = fen_pos(pb, case["fen"])
+        assert sorted(str(m) for m in p.generate_moves(engine)) == case["moves"], case["source"]
+    for case in vectors["move_counts"]:
+        assert len(fen_pos(pb, case["fen"]).generate_moves(engine)) == case["count"], case["source"]
+
+
+def test_move_lists_bit_exact_on_playout_positions(engine, playout_positions):
+    offsets, moves = engine.generate_moves_batch(playout_positions)
+    want_offsets, want_moves = oracle.generate_moves_batch(playout_positions)
+    assert np.array_equal(offsets, want_offsets)
+    assert np.array_equal(moves, want_moves)
+    counts = engine.count_moves_batch(playout_positions)
+    assert np.array_equal(counts, np.diff(want_offsets))
+
+
+def test_empty_and_tiny_batches(engine, playout_positions):
+    offsets, moves = engine.generate_moves_batch(playout_positions[:0])
+    assert offsets.tolist() == [0] and len(moves) == 0
+    assert len(engine.perft_batch(playout_positions[:0], 3)) == 0
+    offsets, moves = engine.generate_moves_batch(playout_positions[:1])
+    assert offsets.tolist() == [0, 20]
+
+
+def test_in_check(engine, playout_positions):
+    got = engine.in_check_batch(playout_positions[:5000])
+    want = [oracle.in_check(oracle.Position.from_buffer_copy(playout_positions[i].tobytes())) for i in range(5000)]
+    assert got.tolist() == want
+
+
+# ---- make_move: children of a ply, field for field (tests/chess.rs:474-531,580-620) ----
+
+def test_reference_make_move_vectors(pb, engine, vectors):
+    for case in vectors["make_move"]:
+        p = fen_pos(pb, case["start"])
+        for step in case["steps"]:
+            if "move" in step:
+                p.make_move(pb.Move.from_uci(step["move"]), engine)
+            else:
+                assert str(p) == step["fen"], case["test"]
+
+
+def test_children_equal_oracle_children(engine, playout_positions):
+    batch = playout_positions[::11][:2500]
+    offsets, children = engine.expand_batch(batch)
+    want_offsets, want_moves = oracle.generate_moves_batch(batch)
+    assert np.array_equal(offsets, want_offsets)
+    k = 0
+    for i in range(len(batch)):
+        parent = oracle.Position.from_buffer_copy(batch[i].tobytes())
+        for m in want_moves[want_offsets[i]:want_offsets[i + 1]]:
+            c = oracle.copy(parent)
+            oracle.make_move(c, int(m))
+            c.hash = 0
+            assert bytes(c) == children[k].tobytes(), (oracle.to_fen(parent), oracle.move_to_uci(int(m)))
+            k += 1
+    assert k == len(children)
+
+
+# ---- text API through the same library (tests/chess.rs:33-181) ----
+
+def test_fen_round_trips_and_errors(pb, vectors):
+    fen = vectors["fen"]
+    for text in fen["roundtrip"]:
+        assert str(pb.Position.from_fen(text)).startswith(text)
