@@ -55,7 +55,11 @@ typedef struct {
   uint64_t algorithmic_bytes; /* 2 * 64 B * interior nodes (perft) or 64N + 4(N+1) + 2M (lists) */
   uint64_t kernel_launches;   /* kernels launched by the call */
   uint64_t interior_nodes;    /* positions for which moves were generated */
-  uint64_t reserved[3];
+  /* the fused last-two-plies kernel (K2), which dominates perft: */
+  double leaf_kernel_ms;      /* sum of its launches' CUDA-event durations */
+  uint64_t leaf_kernel_launches;
+  uint64_t leaf_parents;      /* records it read from HBM (ply depth-2) */
+  uint64_t leaf_children;     /* positions it generated, counted and never wrote out (ply depth-1) */
 } pabi_timing_t;
 
 /* ---- host-side text API (no device work) -------------------------------- */
@@ -113,7 +117,8 @@ int pabi_cuda_count_moves_batch(pabi_cuda_ctx* ctx, const pabi_position_t* posit
 int pabi_cuda_in_check_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, size_t n,
                              uint8_t* in_check /* [n] */, pabi_timing_t* timing);
 /* Position::make_move(&Move), src/chess/position.rs:414-433: out[i] = positions[i] after moves[i]
- * (moves must be legal; the hash field is copied unchanged). */
+ * (moves must be legal; the hash field of every device-produced position is 0: the reference's
+ * Zobrist keys are build-random, generated.rs:15-16, so hash values cannot be reproduced). */
 int pabi_cuda_make_moves_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, const pabi_move_t* moves,
                                size_t n, pabi_position_t* out, pabi_timing_t* timing);
 /* One breadth-first ply: every child of every position, in generate_moves order

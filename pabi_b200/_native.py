@@ -50,12 +50,17 @@ class Timing(C.Structure):
         ("algorithmic_bytes", C.c_uint64),
         ("kernel_launches", C.c_uint64),
         ("interior_nodes", C.c_uint64),
-        ("reserved", C.c_uint64 * 3),
+        ("leaf_kernel_ms", C.c_double),
+        ("leaf_kernel_launches", C.c_uint64),
+        ("leaf_parents", C.c_uint64),
+        ("leaf_children", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:
         return {"device_ms": self.device_ms, "host_ms": self.host_ms, "algorithmic_bytes": self.algorithmic_bytes,
-                "kernel_launches": self.kernel_launches, "interior_nodes": self.interior_nodes}
+                "kernel_launches": self.kernel_launches, "interior_nodes": self.interior_nodes,
+                "leaf_kernel_ms": self.leaf_kernel_ms, "leaf_kernel_launches": self.leaf_kernel_launches,
+                "leaf_parents": self.leaf_parents, "leaf_children": self.leaf_children}
 
 
 class PabiCudaError(RuntimeError):

@@ -47,7 +47,8 @@ PB_HD int popc(u64 x) {
 /* index of the least significant set bit; x != 0 (bitboard.rs:310-322 iterates LS1B first) */
 PB_HD int lsb(u64 x) {
 #ifdef __CUDA_ARCH__
-  return __ffsll((long long)x) - 1;
+  const u32 lo = (u32)x, hi = (u32)(x >> 32); /* 6 SASS instructions instead of __ffsll's 10 */
+  return (lo ? 0 : 32) + __ffs((int)(lo ? lo : hi)) - 1;
 #else
   return __builtin_ctzll(x);
 #endif
@@ -140,6 +141,8 @@ struct SharedTables {
   SliderEntry rook[64];
   u32 bishop_os[64]; /* offset | (32 - bits) << 24 */
   u32 rook_os[64];
+  u64 rook_adj[64];   /* the (up to 4) orthogonal neighbours */
+  u64 bishop_adj[64]; /* the (up to 4) diagonal neighbours */
   u8 keep_from[64]; /* castling rights kept when a move leaves this square (position.rs:435-468) */
   u8 keep_to[64];   /* ... when a move lands on this square */
   u64 bishop_attacks[BISHOP_TABLE_SIZE];
@@ -346,45 +349,159 @@ PB_HD PawnSets pawn_sources(const Pos& p, const TB& tb, const Analysis& a) {
   return s;
 }
 
-/* ---- count only: == generate_moves().len() (position.rs:914-916) -------- */
+/* ---- count only: == generate_moves().len() (position.rs:914-916) --------
+ * This is the function perft spends its time in (one call per node of the last
+ * ply but one), so it is organised to execute as few instructions as possible:
+ *  - the position is first mirrored so that the side to move plays up the board
+ *    (byte-swapped bitboards, swapped castling nibble): a count does not depend
+ *    on the colour, and all colour-dependent shifts and masks become constants;
+ *  - the enemy attack map is only needed on the squares the king could step to
+ *    and on the castling walk; enemy sliders whose empty-board lines miss those
+ *    squares are skipped without a table lookup, and when the king has no
+ *    candidate square at all the whole map is skipped;
+ *  - the x-ray lookups for pins run only when an enemy slider stands on one of
+ *    the king's empty-board lines behind one of our pieces;
+ *  - our sliders hemmed in by our own pieces are skipped.
+ * Every shortcut is exact; tests/test_device_logic_on_host.py compares the
+ * result with the oracle's list length on every node of the reference trees. */
+PB_HD u64 bswap64(u64 x) {
+#ifdef __CUDA_ARCH__
+  const u32 lo = (u32)x, hi = (u32)(x >> 32);
+  return ((u64)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
+#else
+  return __builtin_bswap64(x);
+#endif
+}
+
 template <class TB>
 PB_HD u32 count_moves(const Pos& p, const TB& tb) {
-  Analysis a;
-  analyze(p, tb, a);
-  u32 n = popc(a.safe_king);
-  if (a.block == 0) return n; /* double check: king moves only, position.rs:356 */
-  const u64 targets = ~a.our & a.block;
+  /* mirror to "white to move" */
+  const bool flip = meta_stm(p.meta) != 0;
+  const u64 all = p.pawns | p.knights | p.bishops | p.rooks | p.queens | p.kings;
+  u64 our = flip ? all & ~p.white : p.white;
+  u64 pawns = p.pawns, knights = p.knights, bishops = p.bishops, rooks = p.rooks, queens = p.queens, kings = p.kings;
+  u64 occ = all;
+  int rights = meta_castling(p.meta);
+  int ep = meta_ep(p.meta);
+  if (flip) {
+    our = bswap64(our), pawns = bswap64(pawns), knights = bswap64(knights), bishops = bswap64(bishops);
+    rooks = bswap64(rooks), queens = bswap64(queens), kings = bswap64(kings), occ = bswap64(occ);
+    rights >>= 2;
+    ep ^= 56; /* 64 (none) stays >= 64 */
+  }
+  const u64 their = occ ^ our;
+  const u64 king_bb = kings & our;
+  const int king = lsb(king_bb);
+  const u64 their_diag = (bishops | queens) & their;
+  const u64 their_orth = (rooks | queens) & their;
 
-  for (u64 b = p.knights & a.our & ~a.pins; b; b &= b - 1) n += popc(tb.knight(lsb(b)) & targets);
-  for (u64 b = (p.rooks | p.queens) & a.our; b; b &= b - 1) {
+  const u64 king_diag = tb.bishop(king, occ);
+  const u64 king_orth = tb.rook(king, occ);
+  const u64 checkers = (tb.knight(king) & knights & their) | (pawn_attacks(king_bb, 0) & pawns & their) |
+                       (king_diag & their_diag) | (king_orth & their_orth);
+
+  /* king steps and castling: the only consumers of the enemy attack map */
+  const u64 king_targets = tb.king(king) & ~our;
+  u64 need = king_targets;
+  if (checkers == 0) {
+    if ((rights & 1) && (occ & 0x60ULL) == 0) need |= 0x60ULL;
+    if ((rights & 2) && (occ & 0x0EULL) == 0) need |= 0x0CULL;
+  }
+  u32 n = 0;
+  if (need) {
+    const u64 occ_nk = occ ^ king_bb;
+    u64 att = tb.king(lsb(kings & their)) | pawn_attacks(pawns & their, 1);
+    for (u64 b = knights & their; b; b &= b - 1) att |= tb.knight(lsb(b));
+    for (u64 b = their_diag; b; b &= b - 1) {
+      const int sq = lsb(b);
+      if ((tb.s->diag[sq] | tb.s->anti[sq]) & need) att |= tb.bishop(sq, occ_nk);
+    }
+    for (u64 b = their_orth; b; b &= b - 1) {
+      const int sq = lsb(b);
+      if (((FILE_A << (sq & 7)) | (RANK_1 << (sq & 56))) & need) att |= tb.rook(sq, occ_nk);
+    }
+    n = popc(king_targets & ~att);
+    if (checkers == 0) { /* position.rs:1226-1288, walk masks attacks.rs:203-214 */
+      n += ((rights & 1) && ((att | occ) & 0x60ULL) == 0);
+      n += ((rights & 2) && (att & 0x0CULL) == 0 && (occ & 0x0EULL) == 0);
+    }
+  }
+
+  u64 block = ~0ULL;
+  if (checkers) {
+    if (checkers & (checkers - 1)) return n; /* double check: king moves only, position.rs:356 */
+    const u64 r = tb.ray(lsb(checkers), king);
+    block = r ? r : checkers;
+  }
+
+  u64 pins = 0;
+  {
+    const u64 cand = king_diag & our;
+    if (cand && ((tb.s->diag[king] | tb.s->anti[king]) & their_diag & ~king_diag)) {
+      u64 pinners = tb.bishop(king, occ ^ cand) & ~king_diag & their_diag;
+      for (; pinners; pinners &= pinners - 1) pins |= tb.ray(lsb(pinners), king) & cand;
+    }
+  }
+  {
+    const u64 cand = king_orth & our;
+    if (cand && (((FILE_A << (king & 7)) | (RANK_1 << (king & 56))) & their_orth & ~king_orth)) {
+      u64 pinners = tb.rook(king, occ ^ cand) & ~king_orth & their_orth;
+      for (; pinners; pinners &= pinners - 1) pins |= tb.ray(lsb(pinners), king) & cand;
+    }
+  }
+
+  const u64 not_our = ~our;
+  const u64 targets = not_our & block;
+  for (u64 b = knights & our & ~pins; b; b &= b - 1) n += popc(tb.knight(lsb(b)) & targets);
+  for (u64 b = (rooks | queens) & our; b; b &= b - 1) {
     const int from = lsb(b);
-    u64 t = tb.rook(from, a.occ) & targets;
-    if ((a.pins >> from) & 1) t &= tb.line(a.king, from);
+    if ((tb.s->rook_adj[from] & not_our) == 0) continue; /* hemmed in by our own pieces */
+    u64 t = tb.rook(from, occ) & targets;
+    if ((pins >> from) & 1) t &= tb.line(king, from);
     n += popc(t);
   }
-  for (u64 b = (p.bishops | p.queens) & a.our; b; b &= b - 1) {
+  for (u64 b = (bishops | queens) & our; b; b &= b - 1) {
     const int from = lsb(b);
-    u64 t = tb.bishop(from, a.occ) & targets;
-    if ((a.pins >> from) & 1) t &= tb.line(a.king, from);
+    if ((tb.s->bishop_adj[from] & not_our) == 0) continue;
+    u64 t = tb.bishop(from, occ) & targets;
+    if ((pins >> from) & 1) t &= tb.line(king, from);
     n += popc(t);
   }
 
-  const PawnSets ps = pawn_sources(p, tb, a);
-  const u64 last_rank = a.us == 0 ? RANK_8 : RANK_1;
-  const u64 capture_targets = a.their & a.block;
-  const u64 west = pawn_attacks_west(ps.west, a.us) & capture_targets;
-  const u64 east = pawn_attacks_east(ps.east, a.us) & capture_targets;
-  const u64 empty = ~a.occ;
-  const u64 single_all = push(ps.pushers, a.us) & empty;
-  const u64 single = single_all & a.block;
-  const u64 dbl = push(single_all & (a.us == 0 ? RANK_3 : RANK_6), a.us) & empty & a.block;
+  /* pawns, set-wise (position.rs:1106-1224); a pinned pawn pushes only along the
+   * king's file and captures only along the pin diagonal */
+  const u64 our_pawns = pawns & our;
+  u64 west_src = our_pawns & ~pins, east_src = west_src, pushers = west_src;
+  const u64 pinned = our_pawns & pins;
+  if (pinned) {
+    pushers |= pinned & (FILE_A << (king & 7));
+    west_src |= pinned & tb.s->anti[king];
+    east_src |= pinned & tb.s->diag[king];
+  }
+  const u64 capture_targets = their & block;
+  const u64 west = ((west_src & ~FILE_A) << 7) & capture_targets;
+  const u64 east = ((east_src & ~FILE_H) << 9) & capture_targets;
+  const u64 single_all = (pushers << 8) & ~occ;
+  const u64 single = single_all & block;
+  const u64 dbl = ((single_all & RANK_3) << 8) & ~occ & block;
   n += popc(west) + popc(east) + popc(single) + popc(dbl);
-  const u64 promos = (west | single) & last_rank;
-  if (promos | (east & last_rank))
-    n += 3 * (popc(west & last_rank) + popc(east & last_rank) + popc(single & last_rank));
-  if (meta_ep(p.meta) < NO_SQUARE) n += popc(en_passant_sources(p, tb, a));
-  const int c = castle_moves(p, a);
-  n += (c & 1) + (c >> 1);
+  if ((west | east | single) & RANK_8) n += 3 * (popc(west & RANK_8) + popc(east & RANK_8) + popc(single & RANK_8));
+
+  if (ep < NO_SQUARE) { /* en passant, position.rs:1144-1178 */
+    const u64 ep_bb = bit(ep);
+    const u64 candidates = pawn_attacks(ep_bb, 1) & our_pawns;
+    if (candidates) {
+      const u64 ep_pawn = ep_bb >> 8;
+      if (checkers & ep_pawn) {
+        n += popc(candidates & ~pins);
+      } else {
+        for (u64 b = candidates; b; b &= b - 1) {
+          const u64 after = ((occ & ~(b & (0 - b))) & ~ep_pawn) | ep_bb;
+          n += (tb.bishop(king, after) & their_diag) == 0 && (tb.rook(king, after) & their_orth) == 0;
+        }
+      }
+    }
+  }
   return n;
 }
 

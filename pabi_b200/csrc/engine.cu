@@ -15,6 +15,7 @@
  */
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -66,9 +67,11 @@ struct pabi_cuda_ctx {
   unsigned long long* d_nodes = nullptr;
   size_t nodes_cap = 0;
   Buffer scratch[6];
+  int tile_variant = 0;
   std::string error;
   /* per-call statistics */
-  uint64_t launches = 0, interior = 0;
+  uint64_t launches = 0, interior = 0, leaf_launches = 0, leaf_parents = 0;
+  std::vector<cudaEvent_t> leaf_events; /* begin/end pairs around every k_tile<LEAF> launch */
 };
 
 namespace {
@@ -133,7 +136,19 @@ void ensure_nodes(pabi_cuda_ctx* ctx, size_t n) {
 }
 
 constexpr size_t FLAT_SMEM = sizeof(SharedTables);
-constexpr size_t TILE_SMEM = sizeof(TileShared);
+
+/* Tile-kernel geometries.  Variant 0 is the default; the others exist so that the
+ * choice can be re-measured on the device (environment variable PABI_TILE_VARIANT). */
+using TileDefault = TileConfig<256, 256, 8192, 2>;
+using TileV1 = TileConfig<384, 192, 6144, 2>;
+using TileV2 = TileConfig<512, 256, 8192, 2>;
+using TileV3 = TileConfig<768, 384, 12288, 1>;
+using TileV4 = TileConfig<1024, 512, 16384, 1>;
+using TileV5 = TileConfig<512, 512, 16384, 1>;
+constexpr int TILE_VARIANTS = 6;
+
+template <bool LEAF, bool MULTI, class CFG>
+void launch_tile_cfg(pabi_cuda_ctx* ctx, Frontier in, size_t first, size_t n, const u64* prefix, Frontier out);
 
 /* counts[0..n) of records [first, first+n) of `l`, then prefix[0..n] */
 void count_and_scan(pabi_cuda_ctx* ctx, const u64* rec, size_t stride, size_t first, size_t n, u32* counts, u64* prefix) {
@@ -154,14 +169,48 @@ void count_and_scan(pabi_cuda_ctx* ctx, const u64* rec, size_t stride, size_t fi
   LAUNCHED();
 }
 
+template <bool LEAF, bool MULTI, class CFG>
+void launch_tile_cfg(pabi_cuda_ctx* ctx, Frontier in, size_t first, size_t n, const u64* prefix, Frontier out) {
+  static bool configured[8] = {};
+  if (!configured[ctx->device & 7]) { /* the table image alone exceeds the default 48 KB of dynamic shared memory */
+    CK(cudaFuncSetAttribute(k_tile<LEAF, MULTI, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared<CFG>)));
+    configured[ctx->device & 7] = true;
+  }
+  const int grid = grid_for(ctx, n, CFG::PARENTS, CFG::MIN_BLOCKS);
+  k_tile<LEAF, MULTI, CFG><<<grid, CFG::THREADS, sizeof(TileShared<CFG>), ctx->stream>>>(ctx->dt, in, first, n, prefix, out, ctx->d_nodes,
+                                                                                      ctx->d_visited);
+}
+
 template <bool LEAF>
 void launch_tile(pabi_cuda_ctx* ctx, bool multi, Frontier in, size_t first, size_t n, const u64* prefix, Frontier out) {
-  const int grid = grid_for(ctx, n, TILE_THREADS, 2);
-  if (multi)
-    k_tile<LEAF, true><<<grid, TILE_THREADS, TILE_SMEM, ctx->stream>>>(ctx->dt, in, first, n, prefix, out, ctx->d_nodes, ctx->d_visited);
-  else
-    k_tile<LEAF, false><<<grid, TILE_THREADS, TILE_SMEM, ctx->stream>>>(ctx->dt, in, first, n, prefix, out, ctx->d_nodes, ctx->d_visited);
+  if (LEAF) {
+    while (ctx->leaf_events.size() < 2 * (ctx->leaf_launches + 1)) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      ctx->leaf_events.push_back(e);
+    }
+    CK(cudaEventRecord(ctx->leaf_events[2 * ctx->leaf_launches], ctx->stream));
+  }
+  if (multi) {
+    launch_tile_cfg<LEAF, true, TileDefault>(ctx, in, first, n, prefix, out);
+  } else if (!LEAF) {
+    launch_tile_cfg<false, false, TileDefault>(ctx, in, first, n, prefix, out);
+  } else {
+    switch (ctx->tile_variant) {
+      case 1: launch_tile_cfg<LEAF, false, TileV1>(ctx, in, first, n, prefix, out); break;
+      case 2: launch_tile_cfg<LEAF, false, TileV2>(ctx, in, first, n, prefix, out); break;
+      case 3: launch_tile_cfg<LEAF, false, TileV3>(ctx, in, first, n, prefix, out); break;
+      case 4: launch_tile_cfg<LEAF, false, TileV4>(ctx, in, first, n, prefix, out); break;
+      case 5: launch_tile_cfg<LEAF, false, TileV5>(ctx, in, first, n, prefix, out); break;
+      default: launch_tile_cfg<LEAF, false, TileDefault>(ctx, in, first, n, prefix, out); break;
+    }
+  }
   LAUNCHED();
+  if (LEAF) {
+    CK(cudaEventRecord(ctx->leaf_events[2 * ctx->leaf_launches + 1], ctx->stream));
+    ++ctx->leaf_launches;
+    ctx->leaf_parents += n;
+  }
 }
 
 /* Walks `remaining` plies below the n records of level `lv`, adding leaf counts
@@ -215,7 +264,7 @@ struct CallTimer {
   pabi_cuda_ctx* ctx;
   std::chrono::steady_clock::time_point t0;
   explicit CallTimer(pabi_cuda_ctx* c) : ctx(c), t0(std::chrono::steady_clock::now()) {
-    ctx->launches = 0, ctx->interior = 0;
+    ctx->launches = 0, ctx->interior = 0, ctx->leaf_launches = 0, ctx->leaf_parents = 0;
     ctx->error.clear();
   }
   void begin_device() { CK(cudaEventRecord(ctx->ev0, ctx->stream)); }
@@ -231,6 +280,12 @@ struct CallTimer {
     t->algorithmic_bytes = bytes;
     t->kernel_launches = ctx->launches;
     t->interior_nodes = ctx->interior;
+    for (uint64_t i = 0; i < ctx->leaf_launches; i++) {
+      CK(cudaEventElapsedTime(&ms, ctx->leaf_events[2 * i], ctx->leaf_events[2 * i + 1]));
+      t->leaf_kernel_ms += ms;
+    }
+    t->leaf_kernel_launches = ctx->leaf_launches;
+    t->leaf_parents = ctx->leaf_parents;
   }
 };
 
@@ -315,6 +370,7 @@ int perft_impl(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, int d
     ctx->interior += ctx->h_result[2];
     /* every node of plies 1..d-1 written once and read once at 64 B */
     timer.finish(timing, 2 * 64 * (ctx->interior > n ? ctx->interior - n : 0));
+    if (timing) timing->leaf_children = ctx->h_result[2];
     return 0;
   } catch (const CudaFail& f) {
     return fail(ctx, f);
@@ -364,10 +420,10 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     CK(cudaFuncSetAttribute(k_in_check, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_make_moves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_emit_moves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
-    CK(cudaFuncSetAttribute(k_tile<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
-    CK(cudaFuncSetAttribute(k_tile<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
-    CK(cudaFuncSetAttribute(k_tile<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
-    CK(cudaFuncSetAttribute(k_tile<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+    if (const char* v = std::getenv("PABI_TILE_VARIANT")) {
+      ctx->tile_variant = std::atoi(v);
+      if (ctx->tile_variant < 0 || ctx->tile_variant >= TILE_VARIANTS) ctx->tile_variant = 0;
+    }
   } catch (const CudaFail& f) {
     std::fprintf(stderr, "pabi_cuda_create: %s\n", ctx->error.c_str());
     int code = (int)f.code;
@@ -398,6 +454,7 @@ void pabi_cuda_destroy(pabi_cuda_ctx* ctx) {
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_rook) cudaFree(ctx->d_rook);
   if (ctx->d_rays) cudaFree(ctx->d_rays);
+  for (cudaEvent_t e : ctx->leaf_events) cudaEventDestroy(e);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);

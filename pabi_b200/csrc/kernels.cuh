@@ -329,76 +329,89 @@ __global__ void k_chunk_end(const u64* __restrict__ prefix, size_t start, size_t
 }
 
 /* ---- K1 / K2: tile kernels ------------------------------------------------
- * A block takes TILE_THREADS consecutive parents at a time:
- *   A0  every thread counts the moves of its parent; block exclusive scan
- *   A   every thread generates its parent's moves (reference order) into the
- *       shared pool at its scanned offset, as (parent << 16 | move)
+ * A block takes PARENTS consecutive parents at a time:
+ *   A0  threads 0..PARENTS-1 count the moves of their parent; block exclusive scan
+ *   A   the same threads generate their parent's moves (reference order) into the
+ *       shared pool at the scanned offset, as (parent << 16 | move)
  *   B   every thread takes children from the pool: parent record from shared
  *       memory, make_move in registers, then
  *         K1: store the child record (coalesced SoA) at its global offset
  *         K2: count the child's moves and accumulate -- the children are never
  *             written to HBM
- * If a tile has more children than the pool holds, A/B repeat over windows. */
-constexpr int TILE_THREADS = 256;
-constexpr int POOL_CAP = 8192;
-
-struct TileShared {
-  SharedTables tables;
-  u64 parents[POS_WORDS][TILE_THREADS];
-  u32 pool[POOL_CAP];
-  u32 parent_nodes[TILE_THREADS]; /* K2, multi-root: nodes below each parent */
-  u32 warp_sums[TILE_THREADS / 32 + 1];
-  u64 red[TILE_THREADS / 32];
+ * If a tile has more children than the pool holds, A/B repeat over windows.
+ * The geometry (threads, parents per tile, pool entries, blocks per SM) is a
+ * template parameter so that variants can be timed against each other on the
+ * device (PABI_TILE_VARIANT, see engine.cu). */
+template <int THREADS_, int PARENTS_, int POOL_, int MIN_BLOCKS_>
+struct TileConfig {
+  static constexpr int THREADS = THREADS_, PARENTS = PARENTS_, POOL = POOL_, MIN_BLOCKS = MIN_BLOCKS_;
+  static_assert(PARENTS_ <= THREADS_ && POOL_ >= 256, "a tile's parents need a thread each; the pool must hold one move list");
 };
 
-template <bool LEAF, bool MULTI_ROOT>
-__global__ void __launch_bounds__(TILE_THREADS, 2)
+template <class CFG>
+struct TileShared {
+  SharedTables tables;
+  u64 parents[POS_WORDS][CFG::PARENTS];
+  u32 pool[CFG::POOL];
+  u32 parent_nodes[CFG::PARENTS]; /* K2, multi-root: nodes below each parent */
+  u32 warp_sums[CFG::THREADS / 32 + 1];
+  u64 red[CFG::THREADS / 32];
+};
+
+template <class CFG>
+__device__ __forceinline__ Pos tile_parent(const TileShared<CFG>& sh, int k) {
+  Pos q;
+  q.white = sh.parents[0][k], q.pawns = sh.parents[1][k], q.knights = sh.parents[2][k], q.bishops = sh.parents[3][k];
+  q.rooks = sh.parents[4][k], q.queens = sh.parents[5][k], q.kings = sh.parents[6][k], q.meta = sh.parents[7][k];
+  return q;
+}
+
+template <bool LEAF, bool MULTI_ROOT, class CFG>
+__global__ void __launch_bounds__(CFG::THREADS, CFG::MIN_BLOCKS)
 k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restrict__ prefix, Frontier out,
        unsigned long long* __restrict__ nodes, unsigned long long* __restrict__ visited) {
+  constexpr int THREADS = CFG::THREADS, PARENTS = CFG::PARENTS, POOL = CFG::POOL;
   extern __shared__ __align__(16) unsigned char smem[];
-  TileShared& sh = *reinterpret_cast<TileShared*>(smem);
+  TileShared<CFG>& sh = *reinterpret_cast<TileShared<CFG>*>(smem);
   stage_tables(&sh.tables, dt.image);
   const Tables tb{&sh.tables, dt.g};
   const int tid = threadIdx.x;
   u64 acc = 0;
-  const size_t n_tiles = (n + TILE_THREADS - 1) / TILE_THREADS;
+  const size_t n_tiles = (n + PARENTS - 1) / PARENTS;
 
   for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const size_t i = tile * TILE_THREADS + tid;
-    const bool valid = i < n;
-    Pos p;
+    const size_t i = tile * PARENTS + tid;
+    const bool valid = tid < PARENTS && i < n;
     u32 cnt = 0;
     if (valid) {
-      p = load_pos(in.rec, in.stride, first + i);
+      const Pos p = load_pos(in.rec, in.stride, first + i);
       sh.parents[0][tid] = p.white, sh.parents[1][tid] = p.pawns, sh.parents[2][tid] = p.knights;
       sh.parents[3][tid] = p.bishops, sh.parents[4][tid] = p.rooks, sh.parents[5][tid] = p.queens;
       sh.parents[6][tid] = p.kings, sh.parents[7][tid] = p.meta;
       cnt = count_moves(p, tb);
     }
-    if (LEAF && MULTI_ROOT) sh.parent_nodes[tid] = 0;
+    if (LEAF && MULTI_ROOT && tid < PARENTS) sh.parent_nodes[tid] = 0;
     u32 total;
-    const u32 off = block_exclusive_scan<TILE_THREADS>(cnt, sh.warp_sums, total);
+    const u32 off = block_exclusive_scan<THREADS>(cnt, sh.warp_sums, total);
     if (LEAF && tid == 0 && total) atomicAdd(visited, (unsigned long long)total); /* statistics: positions at the last ply but one */
     /* global index of this tile's first child (K1); prefix comes from the same count */
-    const u64 child_base = LEAF ? 0 : prefix[first + tile * TILE_THREADS] - prefix[first];
+    const u64 child_base = LEAF ? 0 : prefix[first + tile * PARENTS] - prefix[first];
 
-    for (u32 w = 0; w < total; w += POOL_CAP) {
-      if (cnt && off < w + POOL_CAP && off + cnt > w) {
+    for (u32 w = 0; w < total; w += POOL) {
+      if (cnt && off < w + POOL && off + cnt > w) {
         u32 j = off;
-        generate_moves(p, tb, [&](int from, int to, int promo) {
+        /* the parent is re-read from shared memory so that it does not occupy registers during phase B */
+        generate_moves(tile_parent(sh, tid), tb, [&](int from, int to, int promo) {
           const u32 slot = j++ - w; /* wraps to a huge value below the window */
-          if (slot < (u32)POOL_CAP) sh.pool[slot] = ((u32)tid << 16) | pack_move(from, to, promo);
+          if (slot < (u32)POOL) sh.pool[slot] = ((u32)tid << 16) | pack_move(from, to, promo);
         });
       }
       __syncthreads();
-      const u32 end = min(total - w, (u32)POOL_CAP);
-      for (u32 c = tid; c < end; c += TILE_THREADS) {
+      const u32 end = min(total - w, (u32)POOL);
+      for (u32 c = tid; c < end; c += THREADS) {
         const u32 e = sh.pool[c];
         const int parent = e >> 16;
-        Pos q;
-        q.white = sh.parents[0][parent], q.pawns = sh.parents[1][parent], q.knights = sh.parents[2][parent];
-        q.bishops = sh.parents[3][parent], q.rooks = sh.parents[4][parent], q.queens = sh.parents[5][parent];
-        q.kings = sh.parents[6][parent], q.meta = sh.parents[7][parent];
+        Pos q = tile_parent(sh, parent);
         make_move(q, tb, (u16)(e & 0xFFFF));
         if (LEAF) {
           const u32 k = count_moves(q, tb);
@@ -407,7 +420,7 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         } else {
           const size_t o = (size_t)(child_base + w + c);
           store_pos(out.rec, out.stride, o, q);
-          if (MULTI_ROOT) out.roots[o] = in.roots[first + tile * TILE_THREADS + parent];
+          if (MULTI_ROOT) out.roots[o] = in.roots[first + tile * PARENTS + parent];
         }
       }
       __syncthreads();
@@ -417,7 +430,7 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
       __syncthreads();
     }
   }
-  if (LEAF && !MULTI_ROOT) block_add_u64<TILE_THREADS>(acc, sh.red, nodes);
+  if (LEAF && !MULTI_ROOT) block_add_u64<THREADS>(acc, sh.red, nodes);
 }
 
 } /* namespace pabi */

@@ -189,6 +189,7 @@ def positions_array(ps) -> np.ndarray:
 
 def generate_moves_batch(arr: np.ndarray):
     """CSR move lists (offsets[n+1] u32, moves u16) in the reference's order."""
+    arr = np.ascontiguousarray(arr)
     n = len(arr)
     offsets = np.zeros(n + 1, dtype=np.uint32)
     moves = np.zeros(max(1, 256 * min(n, 4096)), dtype=np.uint16)

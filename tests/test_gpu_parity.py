@@ -92,7 +92,7 @@ def test_chunked_search_gives_the_same_counts(pb, small_engine, vectors):
 
 
 def test_perft_batch_matches_oracle_per_root(engine, playout_positions):
-    batch = playout_positions[::37][:600]
+    batch = np.ascontiguousarray(playout_positions[::37][:600])
     for depth in (1, 2, 3):
         got = engine.perft_batch(batch, depth)
         want = [oracle.perft(oracle.Position.from_buffer_copy(batch[i].tobytes()), depth) for i in range(len(batch))]
@@ -100,7 +100,7 @@ def test_perft_batch_matches_oracle_per_root(engine, playout_positions):
 
 
 def test_perft_batch_chunked(small_engine, playout_positions):
-    batch = playout_positions[::53][:300]
+    batch = np.ascontiguousarray(playout_positions[::53][:300])
     got = small_engine.perft_batch(batch, 4)
     want = [oracle.perft(oracle.Position.from_buffer_copy(batch[i].tobytes()), 4) for i in range(len(batch))]
     assert got.tolist() == want
@@ -173,7 +173,7 @@ def test_reference_make_move_vectors(pb, engine, vectors):
 
 
 def test_children_equal_oracle_children(engine, playout_positions):
-    batch = playout_positions[::11][:2500]
+    batch = np.ascontiguousarray(playout_positions[::11][:2500])
     offsets, children = engine.expand_batch(batch)
     want_offsets, want_moves = oracle.generate_moves_batch(batch)
     assert np.array_equal(offsets, want_offsets)

@@ -1,0 +1,69 @@
+"""Join an ncu `--page source --csv` SASS table with nvdisasm line info and
+aggregate executed instructions / stall samples per source line.
+
+    python tools/ncu_lines.py <report.ncu-rep> <lib.so> <mangled-kernel-substring> [top]
+"""
+import csv
+import re
+import subprocess
+import sys
+import tempfile
+from collections import defaultdict
+from pathlib import Path
+
+rep, so, kern = sys.argv[1], sys.argv[2], sys.argv[3]
+top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+tmp = Path(tempfile.mkdtemp())
+subprocess.run(["cuobjdump", "-xelf", "all", str(Path(so).resolve())], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
+cubin = max(tmp.glob("*.cubin"), key=lambda p: p.stat().st_size)
+sass = subprocess.run(["nvdisasm", "--print-line-info", "-c", str(cubin)], capture_output=True, text=True).stdout.splitlines()
+# locate the kernel's text section
+start = next(i for i, l in enumerate(sass) if l.startswith(".text.") and kern in l)
+lines = []  # (offset, file:line, text)
+cur = "?"
+for l in sass[start + 1:]:
+    if l.startswith(".text.") or l.startswith("//-----"):
+        break
+    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+    if m:
+        cur = f"{Path(m.group(1)).name}:{m.group(2)}"
+        continue
+    m = re.match(r"\s*/\*([0-9a-f]+)\*/\s+(.*?);", l)
+    if m:
+        lines.append((int(m.group(1), 16), cur, m.group(2).strip()))
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+hdr = rows[hdr_i]
+col = {h: i for i, h in enumerate(hdr)}
+body = rows[hdr_i + 1:]
+assert len(body) == len(lines), (len(body), len(lines))
+agg = defaultdict(lambda: [0, 0, 0])
+ops = defaultdict(int)
+tot_inst = tot_samp = 0
+for (off, where, text), r in zip(lines, body):
+    inst = int(r[col["Instructions Executed"]])
+    samp = int(r[col["# Samples"]])
+    agg[where][0] += inst
+    agg[where][1] += samp
+    agg[where][2] += 1
+    ops[text.split()[0] if not text.startswith("@") else text.split()[1]] += inst
+    tot_inst += inst
+    tot_samp += samp
+print(f"total warp instructions {tot_inst}, samples {tot_samp}, SASS lines {len(lines)}")
+src_cache = {}
+def src(where):
+    f, n = where.split(":")
+    for d in ("pabi_b200/csrc",):
+        p = Path(d) / f
+        if p.exists():
+            if p not in src_cache:
+                src_cache[p] = p.read_text().splitlines()
+            return src_cache[p][int(n) - 1].strip()[:90]
+    return ""
+print("--- by source line (instructions executed) ---")
+for where, (inst, samp, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    print(f"{100*inst/tot_inst:5.1f}% inst {100*samp/max(1,tot_samp):5.1f}% samp {n:4d} sass  {where:18s} {src(where)}")
+print("--- by opcode ---")
+for op, inst in sorted(ops.items(), key=lambda kv: -kv[1])[:25]:
+    print(f"{100*inst/tot_inst:5.1f}%  {op}")
