@@ -143,6 +143,7 @@ def run_gpu(args) -> None:
     import torch.distributed as dist
 
     import pabi_b200 as pb
+    from pabi_b200 import distributed as D
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -188,21 +189,13 @@ def run_gpu(args) -> None:
         leaf_launches += t.leaf_kernel_launches
         leaf_parents += t.leaf_parents
         leaf_children += t.leaf_children
-    # the one collective of the path: the u64 count reduction (NCCL over NVLink; 8 bytes per rank)
-    total = torch.tensor([my_nodes], dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    # the one collective of the path: the u64 count reduction (NCCL over NVLink; 16 bytes per rank)
+    nodes_total = D.all_reduce_sum_u64(my_nodes, torch.device("cuda", local))
     barrier()
     wall_s = time.perf_counter() - wall0
     clocks = sampler.stop() if sampler else None
-    stats = torch.tensor([device_ms, wall_s * 1e3, leaf_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    counts = torch.tensor([launches], dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-    device_ms_max, wall_ms_max, leaf_ms_max = stats.tolist()
-    nodes_total = int(total.item())
+    device_ms_max, wall_ms_max, leaf_ms_max = D.all_reduce_max([device_ms, wall_s * 1e3, leaf_ms], torch.device("cuda", local))
+    launches_total = D.all_reduce_sum_u64(launches, torch.device("cuda", local))
     expected = NODES.get(depth)
     if expected is not None and nodes_total != expected * args.steps:
         raise SystemExit(f"wrong node count: {nodes_total} != {expected} x {args.steps}")
@@ -229,7 +222,7 @@ def run_gpu(args) -> None:
             "e2e": {"value": nodes_total / (wall_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 112,
                     "d2h_bytes_per_step": 16, "ms_per_step": wall_ms_max / args.steps,
                     "api": "pabi_b200.perft(Position, depth) / Engine.perft_shard -> pabi_cuda_perft[_shard]"},
-            "gpu_launches": int(counts.item()),
+            "gpu_launches": launches_total,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_tile<LEAF=true> (fused last two plies)", "achieved": achieved,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],

@@ -141,8 +141,6 @@ struct SharedTables {
   SliderEntry rook[64];
   u32 bishop_os[64]; /* offset | (32 - bits) << 24 */
   u32 rook_os[64];
-  u64 rook_adj[64];   /* the (up to 4) orthogonal neighbours */
-  u64 bishop_adj[64]; /* the (up to 4) diagonal neighbours */
   u8 keep_from[64]; /* castling rights kept when a move leaves this square (position.rs:435-468) */
   u8 keep_to[64];   /* ... when a move lands on this square */
   u64 bishop_attacks[BISHOP_TABLE_SIZE];
@@ -453,16 +451,18 @@ PB_HD u32 count_moves(const Pos& p, const TB& tb) {
   const u64 not_our = ~our;
   const u64 targets = not_our & block;
   for (u64 b = knights & our & ~pins; b; b &= b - 1) n += popc(tb.knight(lsb(b)) & targets);
-  for (u64 b = (rooks | queens) & our; b; b &= b - 1) {
+  /* sliders hemmed in by our own pieces (no neighbour on their lines that is not ours) have no
+   * moves and need no lookup; found set-wise */
+  const u64 orth_open = (not_our >> 8) | (not_our << 8) | ((not_our >> 1) & ~FILE_H) | ((not_our << 1) & ~FILE_A);
+  const u64 diag_open = (((not_our >> 9) | (not_our << 7)) & ~FILE_H) | (((not_our >> 7) | (not_our << 9)) & ~FILE_A);
+  for (u64 b = (rooks | queens) & our & orth_open; b; b &= b - 1) {
     const int from = lsb(b);
-    if ((tb.s->rook_adj[from] & not_our) == 0) continue; /* hemmed in by our own pieces */
     u64 t = tb.rook(from, occ) & targets;
     if ((pins >> from) & 1) t &= tb.line(king, from);
     n += popc(t);
   }
-  for (u64 b = (bishops | queens) & our; b; b &= b - 1) {
+  for (u64 b = (bishops | queens) & our & diag_open; b; b &= b - 1) {
     const int from = lsb(b);
-    if ((tb.s->bishop_adj[from] & not_our) == 0) continue;
     u64 t = tb.bishop(from, occ) & targets;
     if ((pins >> from) & 1) t &= tb.line(king, from);
     n += popc(t);

@@ -129,8 +129,6 @@ static HostTables* build() {
     }
     s.diag[sq] = d;
     s.anti[sq] = a;
-    s.rook_adj[sq] = s.king[sq] & ~(d | a);
-    s.bishop_adj[sq] = s.king[sq] & (d | a);
     s.keep_from[sq] = s.keep_to[sq] = 15;
   }
   /* position.rs:435-468 (core.rs:604-612: 1 white short, 2 white long, 4 black short, 8 black long) */
