@@ -67,6 +67,9 @@ constexpr int NO_SQUARE = 64;
 /* Move packing, core.rs:24-66: bits 0-5 from, 6-11 to, 12-14 promotion
  * (0 none, 1 N, 2 B, 3 R, 4 Q; core.rs:700-705). */
 constexpr int PROMO_N = 1, PROMO_B = 2, PROMO_R = 3, PROMO_Q = 4;
+/* kind of the moving piece, passed along with a generated move so that make_move_kind does
+ * not have to look the piece up (numbering of PieceKind, core.rs:448-455) */
+constexpr int KIND_PAWN = 0, KIND_KNIGHT = 1, KIND_BISHOP = 2, KIND_ROOK = 3, KIND_QUEEN = 4, KIND_KING = 5;
 PB_HD u16 pack_move(int from, int to, int promo) { return (u16)(from | (to << 6) | (promo << 12)); }
 
 /* ---- the 64-byte device record --------------------------
@@ -129,6 +132,10 @@ struct SliderEntry {
   u64 mask;  /* relevant occupancy, generated/..._relevant_occupancies.rs */
   u64 magic; /* index = offset + (((occ & mask) * magic) >> (64 - bits)) */
 };
+struct SliderIndex {
+  u32 offset; /* start of the square's block, generated/..._attack_offsets.rs */
+  u32 shift;  /* 32 - bits: applied to the high word of the product */
+};
 constexpr int BISHOP_TABLE_SIZE = 5248;  /* generated.rs:30 */
 constexpr int ROOK_TABLE_SIZE = 102400; /* generated.rs:44 */
 
@@ -139,8 +146,13 @@ struct SharedTables {
   u64 anti[64]; /* full a8-h1-direction line through the square */
   SliderEntry bishop[64];
   SliderEntry rook[64];
-  u32 bishop_os[64]; /* offset | (32 - bits) << 24 */
-  u32 rook_os[64];
+  SliderIndex bishop_os[64];
+  SliderIndex rook_os[64];
+  /* for a (white-normalised) king on the square: where an enemy knight / diagonal slider /
+   * orthogonal slider must stand to reach any square next to the king or on its castling walk */
+  u64 knight_zone[64];
+  u64 diag_zone[64];
+  u64 orth_zone[64];
   u8 keep_from[64]; /* castling rights kept when a move leaves this square (position.rs:435-468) */
   u8 keep_to[64];   /* ... when a move lands on this square */
   u64 bishop_attacks[BISHOP_TABLE_SIZE];
@@ -167,17 +179,17 @@ struct Tables {
   PB_HD u64 king(int sq) const { return s->king[sq]; }
   /* attacks.rs:35-41 */
   PB_HD u64 bishop(int sq, u64 occ) const {
-    SliderEntry e = s->bishop[sq];
-    u32 os = s->bishop_os[sq];
-    u32 h = (u32)(((occ & e.mask) * e.magic) >> 32);
-    return s->bishop_attacks[(os & 0xFFFFFFu) + (h >> (os >> 24))];
+    const SliderEntry e = s->bishop[sq];
+    const SliderIndex os = s->bishop_os[sq];
+    const u32 h = (u32)(((occ & e.mask) * e.magic) >> 32);
+    return s->bishop_attacks[os.offset + (h >> os.shift)];
   }
   /* attacks.rs:27-33 */
   PB_HD u64 rook(int sq, u64 occ) const {
-    SliderEntry e = s->rook[sq];
-    u32 os = s->rook_os[sq];
-    u32 h = (u32)(((occ & e.mask) * e.magic) >> 32);
-    return ldg64(g.rook_attacks + (os & 0xFFFFFFu) + (h >> (os >> 24)));
+    const SliderEntry e = s->rook[sq];
+    const SliderIndex os = s->rook_os[sq];
+    const u32 h = (u32)(((occ & e.mask) * e.magic) >> 32);
+    return ldg64(g.rook_attacks + os.offset + (h >> os.shift));
   }
   /* attacks.rs:54-56 */
   PB_HD u64 ray(int from, int to) const { return ldg64(g.rays + from * 64 + to); }
@@ -407,21 +419,23 @@ PB_HD u32 count_moves(const Pos& p, const TB& tb) {
   }
   u32 n = 0;
   if (need) {
+    /* `rem` = squares of `need` no enemy piece attacks; it only shrinks, so every later piece is
+     * tested against fewer squares and the scan stops when nothing is left */
     const u64 occ_nk = occ ^ king_bb;
-    u64 att = tb.king(lsb(kings & their)) | pawn_attacks(pawns & their, 1);
-    for (u64 b = knights & their; b; b &= b - 1) att |= tb.knight(lsb(b));
-    for (u64 b = their_diag; b; b &= b - 1) {
+    u64 rem = need & ~(tb.king(lsb(kings & their)) | pawn_attacks(pawns & their, 1));
+    for (u64 b = knights & their & tb.s->knight_zone[king]; b; b &= b - 1) rem &= ~tb.knight(lsb(b));
+    for (u64 b = their_diag & tb.s->diag_zone[king]; b && rem; b &= b - 1) {
       const int sq = lsb(b);
-      if ((tb.s->diag[sq] | tb.s->anti[sq]) & need) att |= tb.bishop(sq, occ_nk);
+      if ((tb.s->diag[sq] | tb.s->anti[sq]) & rem) rem &= ~tb.bishop(sq, occ_nk);
     }
-    for (u64 b = their_orth; b; b &= b - 1) {
+    for (u64 b = their_orth & tb.s->orth_zone[king]; b && rem; b &= b - 1) {
       const int sq = lsb(b);
-      if (((FILE_A << (sq & 7)) | (RANK_1 << (sq & 56))) & need) att |= tb.rook(sq, occ_nk);
+      if (((FILE_A << (sq & 7)) | (RANK_1 << (sq & 56))) & rem) rem &= ~tb.rook(sq, occ_nk);
     }
-    n = popc(king_targets & ~att);
+    n = popc(king_targets & rem);
     if (checkers == 0) { /* position.rs:1226-1288, walk masks attacks.rs:203-214 */
-      n += ((rights & 1) && ((att | occ) & 0x60ULL) == 0);
-      n += ((rights & 2) && (att & 0x0CULL) == 0 && (occ & 0x0EULL) == 0);
+      n += ((rights & 1) && (occ & 0x60ULL) == 0 && (rem & 0x60ULL) == 0x60ULL);
+      n += ((rights & 2) && (occ & 0x0EULL) == 0 && (rem & 0x0CULL) == 0x0CULL);
     }
   }
 
@@ -506,36 +520,38 @@ PB_HD u32 count_moves(const Pos& p, const TB& tb) {
 }
 
 /* ---- ordered generation (position.rs:317-408; order of SURVEY.md A.3) ---
- * emit(from, to, promotion) is called once per legal move in the reference's
- * order.  Returns the number of moves. */
+ * emit(from, to, promotion, kind) is called once per legal move in the reference's
+ * order; kind = KIND_* of the moving piece.  Returns the number of moves. */
 template <class TB, class Emit>
 PB_HD u32 generate_moves(const Pos& p, const TB& tb, Emit&& emit) {
   Analysis a;
   analyze(p, tb, a);
   u32 n = 0;
   /* generate_king_moves, position.rs:1034-1040 */
-  for (u64 t = a.safe_king; t; t &= t - 1, ++n) emit(a.king, lsb(t), 0);
+  for (u64 t = a.safe_king; t; t &= t - 1, ++n) emit(a.king, lsb(t), 0, KIND_KING);
   if (a.block == 0) return n;
   const u64 targets = ~a.our & a.block;
 
   /* generate_knight_moves, position.rs:1042-1059 */
   for (u64 b = p.knights & a.our & ~a.pins; b; b &= b - 1) {
     const int from = lsb(b);
-    for (u64 t = tb.knight(from) & targets; t; t &= t - 1, ++n) emit(from, lsb(t), 0);
+    for (u64 t = tb.knight(from) & targets; t; t &= t - 1, ++n) emit(from, lsb(t), 0, KIND_KNIGHT);
   }
   /* generate_rook_moves over rooks|queens, position.rs:1061-1081 */
   for (u64 b = (p.rooks | p.queens) & a.our; b; b &= b - 1) {
     const int from = lsb(b);
     u64 t = tb.rook(from, a.occ) & targets;
     if ((a.pins >> from) & 1) t &= tb.line(a.king, from);
-    for (; t; t &= t - 1, ++n) emit(from, lsb(t), 0);
+    const int kind = (p.queens >> from) & 1 ? KIND_QUEEN : KIND_ROOK;
+    for (; t; t &= t - 1, ++n) emit(from, lsb(t), 0, kind);
   }
   /* generate_bishop_moves over bishops|queens, position.rs:1083-1104 */
   for (u64 b = (p.bishops | p.queens) & a.our; b; b &= b - 1) {
     const int from = lsb(b);
     u64 t = tb.bishop(from, a.occ) & targets;
     if ((a.pins >> from) & 1) t &= tb.line(a.king, from);
-    for (; t; t &= t - 1, ++n) emit(from, lsb(t), 0);
+    const int kind = (p.queens >> from) & 1 ? KIND_QUEEN : KIND_BISHOP;
+    for (; t; t &= t - 1, ++n) emit(from, lsb(t), 0, kind);
   }
 
   /* generate_pawn_moves, position.rs:1106-1224 */
@@ -551,16 +567,17 @@ PB_HD u32 generate_moves(const Pos& p, const TB& tb, Emit&& emit) {
     for (; t; t &= t - 1) {
       const int to = lsb(t);
       if ((to >> 3) == last_rank) {
-        emit(from, to, PROMO_Q), emit(from, to, PROMO_R), emit(from, to, PROMO_B), emit(from, to, PROMO_N);
+        emit(from, to, PROMO_Q, KIND_PAWN), emit(from, to, PROMO_R, KIND_PAWN), emit(from, to, PROMO_B, KIND_PAWN),
+            emit(from, to, PROMO_N, KIND_PAWN);
         n += 4;
       } else {
-        emit(from, to, 0), ++n;
+        emit(from, to, 0, KIND_PAWN), ++n;
       }
     }
   }
   /* en passant (:1144-1178) */
   if (meta_ep(p.meta) < NO_SQUARE)
-    for (u64 b = en_passant_sources(p, tb, a); b; b &= b - 1, ++n) emit(lsb(b), meta_ep(p.meta), 0);
+    for (u64 b = en_passant_sources(p, tb, a); b; b &= b - 1, ++n) emit(lsb(b), meta_ep(p.meta), 0, KIND_PAWN);
   /* single pushes in ascending target order (:1180-1204) */
   const u64 empty = ~a.occ;
   const u64 single_all = push(ps.pushers, a.us) & empty;
@@ -568,21 +585,21 @@ PB_HD u32 generate_moves(const Pos& p, const TB& tb, Emit&& emit) {
   for (u64 t = single_all & a.block; t; t &= t - 1) {
     const int to = lsb(t);
     if ((to >> 3) == last_rank) {
-      emit(to + back, to, PROMO_Q), emit(to + back, to, PROMO_R), emit(to + back, to, PROMO_B),
-          emit(to + back, to, PROMO_N);
+      emit(to + back, to, PROMO_Q, KIND_PAWN), emit(to + back, to, PROMO_R, KIND_PAWN),
+          emit(to + back, to, PROMO_B, KIND_PAWN), emit(to + back, to, PROMO_N, KIND_PAWN);
       n += 4;
     } else {
-      emit(to + back, to, 0), ++n;
+      emit(to + back, to, 0, KIND_PAWN), ++n;
     }
   }
   /* double pushes in ascending target order (:1205-1223) */
   for (u64 t = push(single_all & (a.us == 0 ? RANK_3 : RANK_6), a.us) & empty & a.block; t; t &= t - 1, ++n)
-    emit(lsb(t) + 2 * back, lsb(t), 0);
+    emit(lsb(t) + 2 * back, lsb(t), 0, KIND_PAWN);
   /* generate_castle_moves: short, then long (:1236-1286) */
   const int c = castle_moves(p, a);
   const int home = 4 + 56 * a.us;
-  if (c & 1) emit(home, home + 2, 0), ++n;
-  if (c & 2) emit(home, home - 2, 0), ++n;
+  if (c & 1) emit(home, home + 2, 0, KIND_KING), ++n;
+  if (c & 2) emit(home, home - 2, 0, KIND_KING), ++n;
   return n;
 }
 
@@ -660,6 +677,63 @@ PB_HD void make_move(Pos& p, const TB& tb, u16 mv) {
   p.white = white;
   if (us == 1) fullmove = (fullmove + 1) & 0xFFFF; /* :428-430 */
   p.meta = make_meta(castling, ep, us ^ 1, halfmove, fullmove);
+}
+
+/* make_move for the counting path: the moving piece's kind comes with the move, the clocks
+ * (halfmove, fullmove: position.rs:419,428-430) are not maintained because a count does not
+ * read them.  Board, castling rights, en passant square and side to move are exactly those of
+ * make_move (checked node by node in tests/test_device_logic_on_host.py). */
+template <class TB>
+PB_HD void make_move_kind(Pos& p, const TB& tb, u16 mv, int kind) {
+  const int from = mv & 63, to = (mv >> 6) & 63, promo = (mv >> 12) & 7;
+  const u64 fb = bit(from), tbit = bit(to), m = fb | tbit;
+  const int us = meta_stm(p.meta);
+  const int castling = meta_castling(p.meta) & tb.s->keep_from[from] & tb.s->keep_to[to];
+  const int prev_ep = meta_ep(p.meta);
+  int ep = NO_SQUARE;
+  u64 white = p.white & ~tbit;
+  /* handle_capture: whatever stood on `to` (never a king, never ours) is gone */
+  p.pawns &= ~tbit, p.knights &= ~tbit, p.bishops &= ~tbit, p.rooks &= ~tbit, p.queens &= ~tbit;
+  if (kind == KIND_PAWN) {
+    if (to == prev_ep) {
+      const u64 captured = bit((to & 7) + (from & 56));
+      p.pawns &= ~captured;
+      white &= ~captured;
+    }
+    p.pawns ^= fb;
+    if (promo) {
+      if (promo == PROMO_Q) p.queens |= tbit;
+      else if (promo == PROMO_R) p.rooks |= tbit;
+      else if (promo == PROMO_B) p.bishops |= tbit;
+      else p.knights |= tbit;
+    } else {
+      p.pawns |= tbit;
+      if ((from ^ to) == 16) {
+        const u64 their_pawns = p.pawns & (us == 0 ? ~white : white) & ~tbit;
+        if (pawn_attacks(bit((from + to) >> 1), us) & their_pawns) ep = (from + to) >> 1;
+      }
+    }
+  } else if (kind == KIND_KING) {
+    const int backrank = 56 * us;
+    if (from == backrank + 4 && (to & 56) == backrank && ((to & 7) == 6 || (to & 7) == 2)) {
+      const u64 home = ((to & 7) == 6 ? 0x80ULL : 0x01ULL) << backrank, dest = ((to & 7) == 6 ? 0x20ULL : 0x08ULL) << backrank;
+      const u64 our_home_rook = p.rooks & home & (us == 0 ? white : ~white);
+      p.rooks = (p.rooks ^ our_home_rook) | dest;
+      if (us == 0) white = (white ^ our_home_rook) | dest;
+    }
+    p.kings ^= m;
+  } else if (kind == KIND_KNIGHT) {
+    p.knights ^= m;
+  } else if (kind == KIND_BISHOP) {
+    p.bishops ^= m;
+  } else if (kind == KIND_ROOK) {
+    p.rooks ^= m;
+  } else {
+    p.queens ^= m;
+  }
+  if (us == 0) white = (white & ~fb) | tbit;
+  p.white = white;
+  p.meta = make_meta(castling, ep, us ^ 1, 0, 0);
 }
 
 } /* namespace pabi */

@@ -171,7 +171,7 @@ k_emit_moves(DeviceTables dt, const u64* __restrict__ rec, size_t stride, size_t
     }
     if (prefix[i + 1] > moves_cap) continue;
     u16* dst = moves + base;
-    generate_moves(load_pos(rec, stride, i), tb, [&](int from, int to, int promo) { *dst++ = pack_move(from, to, promo); });
+    generate_moves(load_pos(rec, stride, i), tb, [&](int from, int to, int promo, int) { *dst++ = pack_move(from, to, promo); });
   }
 }
 
@@ -332,7 +332,7 @@ __global__ void k_chunk_end(const u64* __restrict__ prefix, size_t start, size_t
  * A block takes PARENTS consecutive parents at a time:
  *   A0  threads 0..PARENTS-1 count the moves of their parent; block exclusive scan
  *   A   the same threads generate their parent's moves (reference order) into the
- *       shared pool at the scanned offset, as (parent << 16 | move)
+ *       shared pool at the scanned offset, as (kind << 28 | parent << 16 | move)
  *   B   every thread takes children from the pool: parent record from shared
  *       memory, make_move in registers, then
  *         K1: store the child record (coalesced SoA) at its global offset
@@ -345,7 +345,7 @@ __global__ void k_chunk_end(const u64* __restrict__ prefix, size_t start, size_t
 template <int THREADS_, int PARENTS_, int POOL_, int MIN_BLOCKS_>
 struct TileConfig {
   static constexpr int THREADS = THREADS_, PARENTS = PARENTS_, POOL = POOL_, MIN_BLOCKS = MIN_BLOCKS_;
-  static_assert(PARENTS_ <= THREADS_ && POOL_ >= 256, "a tile's parents need a thread each; the pool must hold one move list");
+  static_assert(PARENTS_ <= THREADS_ && PARENTS_ <= 4096 && POOL_ >= 256, "a tile's parents need a thread each; the pool must hold one move list");
 };
 
 template <class CFG>
@@ -401,23 +401,24 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
       if (cnt && off < w + POOL && off + cnt > w) {
         u32 j = off;
         /* the parent is re-read from shared memory so that it does not occupy registers during phase B */
-        generate_moves(tile_parent(sh, tid), tb, [&](int from, int to, int promo) {
+        generate_moves(tile_parent(sh, tid), tb, [&](int from, int to, int promo, int kind) {
           const u32 slot = j++ - w; /* wraps to a huge value below the window */
-          if (slot < (u32)POOL) sh.pool[slot] = ((u32)tid << 16) | pack_move(from, to, promo);
+          if (slot < (u32)POOL) sh.pool[slot] = ((u32)kind << 28) | ((u32)tid << 16) | pack_move(from, to, promo);
         });
       }
       __syncthreads();
       const u32 end = min(total - w, (u32)POOL);
       for (u32 c = tid; c < end; c += THREADS) {
         const u32 e = sh.pool[c];
-        const int parent = e >> 16;
+        const int parent = (e >> 16) & 0xFFF;
         Pos q = tile_parent(sh, parent);
-        make_move(q, tb, (u16)(e & 0xFFFF));
         if (LEAF) {
+          make_move_kind(q, tb, (u16)(e & 0xFFFF), (int)(e >> 28));
           const u32 k = count_moves(q, tb);
           if (MULTI_ROOT) atomicAdd(&sh.parent_nodes[parent], k);
           else acc += k;
         } else {
+          make_move(q, tb, (u16)(e & 0xFFFF));
           const size_t o = (size_t)(child_base + w + c);
           store_pos(out.rec, out.stride, o, q);
           if (MULTI_ROOT) out.roots[o] = in.roots[first + tile * PARENTS + parent];

@@ -142,16 +142,25 @@ static HostTables* build() {
     const u64 bm = relevant_mask(sq, BISHOP_DIRS), rm = relevant_mask(sq, ROOK_DIRS);
     s.bishop[sq].mask = bm;
     s.bishop[sq].magic = build_slider(sq, BISHOP_DIRS, bm, s.bishop_attacks + boff, rng);
-    s.bishop_os[sq] = boff | (u32)(32 - popc(bm)) << 24;
+    s.bishop_os[sq] = SliderIndex{boff, (u32)(32 - popc(bm))};
     boff += 1u << popc(bm);
     s.rook[sq].mask = rm;
     s.rook[sq].magic = build_slider(sq, ROOK_DIRS, rm, t->rook_attacks + roff, rng);
-    s.rook_os[sq] = roff | (u32)(32 - popc(rm)) << 24;
+    s.rook_os[sq] = SliderIndex{roff, (u32)(32 - popc(rm))};
     roff += 1u << popc(rm);
   }
   if (boff != BISHOP_TABLE_SIZE || roff != ROOK_TABLE_SIZE) {
     std::fprintf(stderr, "pabi_b200: slider table sizes %u/%u differ from generated.rs:30,44\n", boff, roff);
     std::abort();
+  }
+  for (int k = 0; k < 64; k++) { /* zones: the king's neighbours, plus the castling walk for a king on e1 */
+    const u64 zone = s.king[k] | (k == 4 ? 0x6CULL : 0);
+    for (u64 z = zone; z; z &= z - 1) {
+      const int t = lsb(z);
+      s.knight_zone[k] |= s.knight[t];
+      s.diag_zone[k] |= s.diag[t] | s.anti[t];
+      s.orth_zone[k] |= (FILE_A << (t & 7)) | (RANK_1 << (t & 56));
+    }
   }
   /* RAYS (attacks.rs:486-553): from inclusive, towards `to`, `to` exclusive */
   for (int from = 0; from < 64; from++)

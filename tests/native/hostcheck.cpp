@@ -25,7 +25,7 @@ uint32_t hostcheck_count_moves(const pabi_position_t* p) { return count_moves(pa
 
 uint32_t hostcheck_generate_moves(const pabi_position_t* p, uint16_t* out) {
   uint32_t k = 0;
-  return generate_moves(pack_record(*p), host_tb(), [&](int f, int t, int pr) { out[k++] = pack_move(f, t, pr); });
+  return generate_moves(pack_record(*p), host_tb(), [&](int f, int t, int pr, int) { out[k++] = pack_move(f, t, pr); });
 }
 
 void hostcheck_make_move(pabi_position_t* p, uint16_t mv) {
@@ -50,12 +50,13 @@ static uint64_t perft_rec(const Pos& p, const Tables& tb, int depth) {
   if (depth == 0) return 1;
   if (depth == 1) return count_moves(p, tb);
   uint16_t moves[256];
+  int kinds[256];
   uint32_t k = 0;
-  generate_moves(p, tb, [&](int f, int t, int pr) { moves[k++] = pack_move(f, t, pr); });
+  generate_moves(p, tb, [&](int f, int t, int pr, int kind) { kinds[k] = kind, moves[k++] = pack_move(f, t, pr); });
   uint64_t n = 0;
   for (uint32_t i = 0; i < k; i++) {
     Pos c = p;
-    make_move(c, tb, moves[i]);
+    make_move_kind(c, tb, moves[i], kinds[i]); /* the path the leaf kernel takes */
     n += perft_rec(c, tb, depth - 1);
   }
   return n;
@@ -77,7 +78,8 @@ static uint64_t walk_compare(const pabi_position_t& p, int depth, oracle_gen_fn 
   const Tables tb = host_tb();
   const Pos r = pack_record(p);
   uint32_t k = 0;
-  const uint32_t ng = generate_moves(r, tb, [&](int f, int t, int pr) { got[k++] = pack_move(f, t, pr); });
+  int kinds[256];
+  const uint32_t ng = generate_moves(r, tb, [&](int f, int t, int pr, int kind) { kinds[k] = kind, got[k++] = pack_move(f, t, pr); });
   uint64_t bad = 0;
   if (ng != nw || count_moves(r, tb) != nw) bad = 1;
   for (uint32_t i = 0; i < nw && !bad; i++)
@@ -93,7 +95,12 @@ static uint64_t walk_compare(const pabi_position_t& p, int depth, oracle_gen_fn 
     Pos c = r;
     make_move(c, tb, want[i]);
     b = unpack_record(c, a.hash);
-    if (__builtin_memcmp(&a, &b, sizeof a) != 0) {
+    Pos ck = r; /* the counting path's make_move: same board, rights, ep square, side to move */
+    make_move_kind(ck, tb, want[i], kinds[i]);
+    const bool same_kind = ck.white == c.white && ck.pawns == c.pawns && ck.knights == c.knights && ck.bishops == c.bishops &&
+                           ck.rooks == c.rooks && ck.queens == c.queens && ck.kings == c.kings &&
+                           (ck.meta & 0xFFFF) == (c.meta & 0xFFFF);
+    if (__builtin_memcmp(&a, &b, sizeof a) != 0 || !same_kind) {
       if (first_bad) *first_bad = p;
       return bad + 1;
     }
@@ -128,7 +135,7 @@ uint64_t hostcheck_rook(int sq, uint64_t occ) { return host_tb().rook(sq, occ); 
 void hostcheck_slider_entry(int rook, int sq, uint64_t* mask, uint32_t* offset, uint32_t* bits) {
   const SharedTables& s = host_tables().shared;
   *mask = rook ? s.rook[sq].mask : s.bishop[sq].mask;
-  uint32_t os = rook ? s.rook_os[sq] : s.bishop_os[sq];
-  *offset = os & 0xFFFFFF, *bits = 32 - (os >> 24);
+  const SliderIndex os = rook ? s.rook_os[sq] : s.bishop_os[sq];
+  *offset = os.offset, *bits = 32 - os.shift;
 }
 }

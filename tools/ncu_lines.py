@@ -16,21 +16,28 @@ top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 tmp = Path(tempfile.mkdtemp())
 subprocess.run(["cuobjdump", "-xelf", "all", str(Path(so).resolve())], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
 cubin = max(tmp.glob("*.cubin"), key=lambda p: p.stat().st_size)
-sass = subprocess.run(["nvdisasm", "--print-line-info", "-c", str(cubin)], capture_output=True, text=True).stdout.splitlines()
+sass = subprocess.run(["nvdisasm", "--print-line-info-inline", "-c", str(cubin)], capture_output=True, text=True).stdout.splitlines()
 # locate the kernel's text section
 start = next(i for i, l in enumerate(sass) if l.startswith(".text.") and kern in l)
 lines = []  # (offset, file:line, text)
-cur = "?"
+chains = []  # per instruction: inline chain, innermost first
+cur, chain, fresh = "?", [], True
 for l in sass[start + 1:]:
     if l.startswith(".text.") or l.startswith("//-----"):
         break
-    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
-    if m:
-        cur = f"{Path(m.group(1)).name}:{m.group(2)}"
+    found = re.findall(r'File "([^"]+)", line (\d+)', l)
+    if l.lstrip().startswith("//## File") and found:
+        if fresh:
+            chain, fresh = [], False
+        for f, n in found:
+            chain.append(f"{Path(f).name}:{n}")
+        cur = chain[0]
         continue
     m = re.match(r"\s*/\*([0-9a-f]+)\*/\s+(.*?);", l)
     if m:
         lines.append((int(m.group(1), 16), cur, m.group(2).strip()))
+        chains.append(list(dict.fromkeys(chain)))
+        fresh = True
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
@@ -64,6 +71,21 @@ def src(where):
 print("--- by source line (instructions executed) ---")
 for where, (inst, samp, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     print(f"{100*inst/tot_inst:5.1f}% inst {100*samp/max(1,tot_samp):5.1f}% samp {n:4d} sass  {where:18s} {src(where)}")
+def outer(chain, fname):
+    """outermost frame of the chain that lies in `fname`"""
+    for fr in reversed(chain):
+        if fr.startswith(fname + ":"):
+            return fr
+    return chain[-1] if chain else "?"
+for fname, title in (("chess.cuh", "by outermost chess.cuh line (callers of the helpers)"), ("kernels.cuh", "by kernel line")):
+    agg2 = defaultdict(lambda: [0, 0])
+    for ch, r in zip(chains, body):
+        k = outer(ch, fname)
+        agg2[k][0] += int(r[col["Instructions Executed"]])
+        agg2[k][1] += int(r[col["# Samples"]])
+    print(f"--- {title} ---")
+    for where, (inst, samp) in sorted(agg2.items(), key=lambda kv: -kv[1][0])[:top]:
+        print(f"{100*inst/tot_inst:5.1f}% inst {100*samp/max(1,tot_samp):5.1f}% samp  {where:18s} {src(where)}")
 print("--- by opcode ---")
 for op, inst in sorted(ops.items(), key=lambda kv: -kv[1])[:25]:
     print(f"{100*inst/tot_inst:5.1f}%  {op}")
