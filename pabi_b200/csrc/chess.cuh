@@ -238,9 +238,9 @@ struct Analysis {
  *    enemy sliders that appear when they are removed; "exactly one blocker and
  *    it is ours" (attacks.rs:147-156) is the same condition.
  *  - xrays (attacks.rs:93) are not computed: move generation never reads them. */
-template <class TB>
+template <int US = -1, class TB>
 PB_HD void analyze(const Pos& p, const TB& tb, Analysis& a) {
-  const int us = meta_stm(p.meta);
+  const int us = US >= 0 ? US : meta_stm(p.meta); /* US: side to move when known at compile time */
   const int them = us ^ 1;
   const u64 occ = p.pawns | p.knights | p.bishops | p.rooks | p.queens | p.kings;
   const u64 our = us == 0 ? p.white : occ & ~p.white;
@@ -383,22 +383,13 @@ PB_HD u64 bswap64(u64 x) {
 #endif
 }
 
+/* The count for a position that is already "white to move": `our` = the mover's occupancy, the
+ * piece sets merged over both colours, `rights` = the mover's castling bits (1 short, 2 long),
+ * `ep` = en passant square (>= 64: none). */
 template <class TB>
-PB_HD u32 count_moves(const Pos& p, const TB& tb) {
-  /* mirror to "white to move" */
-  const bool flip = meta_stm(p.meta) != 0;
-  const u64 all = p.pawns | p.knights | p.bishops | p.rooks | p.queens | p.kings;
-  u64 our = flip ? all & ~p.white : p.white;
-  u64 pawns = p.pawns, knights = p.knights, bishops = p.bishops, rooks = p.rooks, queens = p.queens, kings = p.kings;
-  u64 occ = all;
-  int rights = meta_castling(p.meta);
-  int ep = meta_ep(p.meta);
-  if (flip) {
-    our = bswap64(our), pawns = bswap64(pawns), knights = bswap64(knights), bishops = bswap64(bishops);
-    rooks = bswap64(rooks), queens = bswap64(queens), kings = bswap64(kings), occ = bswap64(occ);
-    rights >>= 2;
-    ep ^= 56; /* 64 (none) stays >= 64 */
-  }
+PB_HD u32 count_moves_white(u64 our, u64 pawns, u64 knights, u64 bishops, u64 rooks, u64 queens, u64 kings, int rights,
+                            int ep, const TB& tb) {
+  const u64 occ = pawns | knights | bishops | rooks | queens | kings;
   const u64 their = occ ^ our;
   const u64 king_bb = kings & our;
   const int king = lsb(king_bb);
@@ -519,13 +510,38 @@ PB_HD u32 count_moves(const Pos& p, const TB& tb) {
   return n;
 }
 
+/* The board seen from the other side: ranks mirrored, colours swapped, castling nibbles swapped,
+ * en passant square mirrored.  Legal move counts are invariant under it. */
+PB_HD Pos mirror(const Pos& p) {
+  Pos r;
+  const u64 all = p.pawns | p.knights | p.bishops | p.rooks | p.queens | p.kings;
+  r.white = bswap64(all & ~p.white);
+  r.pawns = bswap64(p.pawns), r.knights = bswap64(p.knights), r.bishops = bswap64(p.bishops);
+  r.rooks = bswap64(p.rooks), r.queens = bswap64(p.queens), r.kings = bswap64(p.kings);
+  const int c = meta_castling(p.meta), ep = meta_ep(p.meta);
+  r.meta = make_meta(((c >> 2) | (c << 2)) & 15, ep < NO_SQUARE ? ep ^ 56 : NO_SQUARE, meta_stm(p.meta) ^ 1,
+                     meta_halfmove(p.meta), meta_fullmove(p.meta));
+  return r;
+}
+
+/* generate_moves().len() of any position */
+template <class TB>
+PB_HD u32 count_moves(const Pos& p, const TB& tb) {
+  if (meta_stm(p.meta) == 0)
+    return count_moves_white(p.white, p.pawns, p.knights, p.bishops, p.rooks, p.queens, p.kings, meta_castling(p.meta) & 3,
+                             meta_ep(p.meta), tb);
+  const Pos m = mirror(p);
+  return count_moves_white(m.white, m.pawns, m.knights, m.bishops, m.rooks, m.queens, m.kings, meta_castling(m.meta) & 3,
+                           meta_ep(m.meta), tb);
+}
+
 /* ---- ordered generation (position.rs:317-408; order of SURVEY.md A.3) ---
  * emit(from, to, promotion, kind) is called once per legal move in the reference's
  * order; kind = KIND_* of the moving piece.  Returns the number of moves. */
-template <class TB, class Emit>
+template <int US = -1, class TB, class Emit>
 PB_HD u32 generate_moves(const Pos& p, const TB& tb, Emit&& emit) {
   Analysis a;
-  analyze(p, tb, a);
+  analyze<US>(p, tb, a);
   u32 n = 0;
   /* generate_king_moves, position.rs:1034-1040 */
   for (u64 t = a.safe_king; t; t &= t - 1, ++n) emit(a.king, lsb(t), 0, KIND_KING);
@@ -683,11 +699,11 @@ PB_HD void make_move(Pos& p, const TB& tb, u16 mv) {
  * (halfmove, fullmove: position.rs:419,428-430) are not maintained because a count does not
  * read them.  Board, castling rights, en passant square and side to move are exactly those of
  * make_move (checked node by node in tests/test_device_logic_on_host.py). */
-template <class TB>
+template <int US = -1, class TB>
 PB_HD void make_move_kind(Pos& p, const TB& tb, u16 mv, int kind) {
   const int from = mv & 63, to = (mv >> 6) & 63, promo = (mv >> 12) & 7;
   const u64 fb = bit(from), tbit = bit(to), m = fb | tbit;
-  const int us = meta_stm(p.meta);
+  const int us = US >= 0 ? US : meta_stm(p.meta); /* US: the mover's colour when known at compile time */
   const int castling = meta_castling(p.meta) & tb.s->keep_from[from] & tb.s->keep_to[to];
   const int prev_ep = meta_ep(p.meta);
   int ep = NO_SQUARE;

@@ -384,11 +384,14 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
     const bool valid = tid < PARENTS && i < n;
     u32 cnt = 0;
     if (valid) {
-      const Pos p = load_pos(in.rec, in.stride, first + i);
+      Pos p = load_pos(in.rec, in.stride, first + i);
+      cnt = count_moves(p, tb);
+      /* K2 keeps the parent with BLACK to move (mirrored if necessary): every child is then "white
+       * to move", which is what count_moves_white wants, and the mover's colour is a constant */
+      if (LEAF && meta_stm(p.meta) == 0) p = mirror(p);
       sh.parents[0][tid] = p.white, sh.parents[1][tid] = p.pawns, sh.parents[2][tid] = p.knights;
       sh.parents[3][tid] = p.bishops, sh.parents[4][tid] = p.rooks, sh.parents[5][tid] = p.queens;
       sh.parents[6][tid] = p.kings, sh.parents[7][tid] = p.meta;
-      cnt = count_moves(p, tb);
     }
     if (LEAF && MULTI_ROOT && tid < PARENTS) sh.parent_nodes[tid] = 0;
     u32 total;
@@ -401,7 +404,7 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
       if (cnt && off < w + POOL && off + cnt > w) {
         u32 j = off;
         /* the parent is re-read from shared memory so that it does not occupy registers during phase B */
-        generate_moves(tile_parent(sh, tid), tb, [&](int from, int to, int promo, int kind) {
+        generate_moves<LEAF ? 1 : -1>(tile_parent(sh, tid), tb, [&](int from, int to, int promo, int kind) {
           const u32 slot = j++ - w; /* wraps to a huge value below the window */
           if (slot < (u32)POOL) sh.pool[slot] = ((u32)kind << 28) | ((u32)tid << 16) | pack_move(from, to, promo);
         });
@@ -413,8 +416,9 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         const int parent = (e >> 16) & 0xFFF;
         Pos q = tile_parent(sh, parent);
         if (LEAF) {
-          make_move_kind(q, tb, (u16)(e & 0xFFFF), (int)(e >> 28));
-          const u32 k = count_moves(q, tb);
+          make_move_kind<1>(q, tb, (u16)(e & 0xFFFF), (int)(e >> 28));
+          const u32 k = count_moves_white(q.white, q.pawns, q.knights, q.bishops, q.rooks, q.queens, q.kings,
+                                          meta_castling(q.meta) & 3, meta_ep(q.meta), tb);
           if (MULTI_ROOT) atomicAdd(&sh.parent_nodes[parent], k);
           else acc += k;
         } else {
