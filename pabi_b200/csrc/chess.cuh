@@ -144,6 +144,8 @@ struct SharedTables {
   u64 king[64];
   u64 diag[64]; /* full a1-h8-direction line through the square (square included) */
   u64 anti[64]; /* full a8-h1-direction line through the square */
+  u64 orth[64]; /* the square's rank and file (a table load is cheaper than two variable 64-bit shifts on
+                   the ALU pipe, which is the pipe this code saturates) */
   SliderEntry bishop[64];
   SliderEntry rook[64];
   SliderIndex bishop_os[64];
@@ -421,7 +423,7 @@ PB_HD u32 count_moves_white(u64 our, u64 pawns, u64 knights, u64 bishops, u64 ro
     }
     for (u64 b = their_orth & tb.s->orth_zone[king]; b && rem; b &= b - 1) {
       const int sq = lsb(b);
-      if (((FILE_A << (sq & 7)) | (RANK_1 << (sq & 56))) & rem) rem &= ~tb.rook(sq, occ_nk);
+      if (tb.s->orth[sq] & rem) rem &= ~tb.rook(sq, occ_nk);
     }
     n = popc(king_targets & rem);
     if (checkers == 0) { /* position.rs:1226-1288, walk masks attacks.rs:203-214 */
@@ -447,7 +449,7 @@ PB_HD u32 count_moves_white(u64 our, u64 pawns, u64 knights, u64 bishops, u64 ro
   }
   {
     const u64 cand = king_orth & our;
-    if (cand && (((FILE_A << (king & 7)) | (RANK_1 << (king & 56))) & their_orth & ~king_orth)) {
+    if (cand && (tb.s->orth[king] & their_orth & ~king_orth)) {
       u64 pinners = tb.rook(king, occ ^ cand) & ~king_orth & their_orth;
       for (; pinners; pinners &= pinners - 1) pins |= tb.ray(lsb(pinners), king) & cand;
     }

@@ -141,7 +141,7 @@ constexpr size_t FLAT_SMEM = sizeof(SharedTables);
  * choice can be re-measured on the device (environment variable PABI_TILE_VARIANT). */
 using TileDefault = TileConfig<1024, 1024, 16384, 1>; /* 64 registers/thread, 32 warps per SM */
 using TileV1 = TileConfig<256, 256, 8192, 2>;
-using TileV2 = TileConfig<512, 256, 8192, 2>;
+using TileV2 = TileConfig<512, 512, 6144, 2>;
 using TileV3 = TileConfig<768, 768, 12288, 1>;
 using TileV4 = TileConfig<1024, 512, 16384, 1>;
 using TileV5 = TileConfig<1024, 1024, 24576, 1>;

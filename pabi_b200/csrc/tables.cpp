@@ -129,6 +129,7 @@ static HostTables* build() {
     }
     s.diag[sq] = d;
     s.anti[sq] = a;
+    s.orth[sq] = (FILE_A << (sq & 7)) | (RANK_1 << (sq & 56));
     s.keep_from[sq] = s.keep_to[sq] = 15;
   }
   /* position.rs:435-468 (core.rs:604-612: 1 white short, 2 white long, 4 black short, 8 black long) */
