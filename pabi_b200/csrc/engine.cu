@@ -147,9 +147,6 @@ using TileV4 = TileConfig<1024, 512, 16384, 1>;
 using TileV5 = TileConfig<1024, 1024, 24576, 1>;
 constexpr int TILE_VARIANTS = 6;
 
-template <bool LEAF, bool MULTI, class CFG>
-void launch_tile_cfg(pabi_cuda_ctx* ctx, Frontier in, size_t first, size_t n, const u64* prefix, Frontier out);
-
 /* counts[0..n) of records [first, first+n) of `l`, then prefix[0..n] */
 void count_and_scan(pabi_cuda_ctx* ctx, const u64* rec, size_t stride, size_t first, size_t n, u32* counts, u64* prefix) {
   k_count<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, rec, stride, first, n, counts);
@@ -169,48 +166,55 @@ void count_and_scan(pabi_cuda_ctx* ctx, const u64* rec, size_t stride, size_t fi
   LAUNCHED();
 }
 
-template <bool LEAF, bool MULTI, class CFG>
-void launch_tile_cfg(pabi_cuda_ctx* ctx, Frontier in, size_t first, size_t n, const u64* prefix, Frontier out) {
+template <TileMode MODE, bool MULTI, class CFG>
+void launch_tile_cfg(pabi_cuda_ctx* ctx, Frontier in, size_t first, size_t n, const u64* prefix, TileOut out) {
   static bool configured[8] = {};
   if (!configured[ctx->device & 7]) { /* the table image alone exceeds the default 48 KB of dynamic shared memory */
-    CK(cudaFuncSetAttribute(k_tile<LEAF, MULTI, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared<CFG>)));
+    CK(cudaFuncSetAttribute(k_tile<MODE, MULTI, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared<CFG>)));
     configured[ctx->device & 7] = true;
   }
   const int grid = grid_for(ctx, n, CFG::PARENTS, CFG::MIN_BLOCKS);
-  k_tile<LEAF, MULTI, CFG><<<grid, CFG::THREADS, sizeof(TileShared<CFG>), ctx->stream>>>(ctx->dt, in, first, n, prefix, out, ctx->d_nodes,
-                                                                                      ctx->d_visited);
+  k_tile<MODE, MULTI, CFG><<<grid, CFG::THREADS, sizeof(TileShared<CFG>), ctx->stream>>>(ctx->dt, in, first, n, prefix, out);
+  LAUNCHED();
 }
 
-template <bool LEAF>
-void launch_tile(pabi_cuda_ctx* ctx, bool multi, Frontier in, size_t first, size_t n, const u64* prefix, Frontier out) {
-  if (LEAF) {
-    while (ctx->leaf_events.size() < 2 * (ctx->leaf_launches + 1)) {
-      cudaEvent_t e;
-      CK(cudaEventCreate(&e));
-      ctx->leaf_events.push_back(e);
-    }
-    CK(cudaEventRecord(ctx->leaf_events[2 * ctx->leaf_launches], ctx->stream));
+/* K2: the last two plies below the n records of `in` */
+void launch_leaf(pabi_cuda_ctx* ctx, bool multi, Frontier in, size_t n) {
+  while (ctx->leaf_events.size() < 2 * (ctx->leaf_launches + 1)) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    ctx->leaf_events.push_back(e);
   }
+  CK(cudaEventRecord(ctx->leaf_events[2 * ctx->leaf_launches], ctx->stream));
+  const TileOut out{Frontier{nullptr, nullptr, 0}, nullptr, nullptr, ctx->d_nodes, ctx->d_visited};
   if (multi) {
-    launch_tile_cfg<LEAF, true, TileDefault>(ctx, in, first, n, prefix, out);
-  } else if (!LEAF) {
-    launch_tile_cfg<false, false, TileDefault>(ctx, in, first, n, prefix, out);
+    launch_tile_cfg<TILE_LEAF, true, TileDefault>(ctx, in, 0, n, nullptr, out);
   } else {
     switch (ctx->tile_variant) {
-      case 1: launch_tile_cfg<LEAF, false, TileV1>(ctx, in, first, n, prefix, out); break;
-      case 2: launch_tile_cfg<LEAF, false, TileV2>(ctx, in, first, n, prefix, out); break;
-      case 3: launch_tile_cfg<LEAF, false, TileV3>(ctx, in, first, n, prefix, out); break;
-      case 4: launch_tile_cfg<LEAF, false, TileV4>(ctx, in, first, n, prefix, out); break;
-      case 5: launch_tile_cfg<LEAF, false, TileV5>(ctx, in, first, n, prefix, out); break;
-      default: launch_tile_cfg<LEAF, false, TileDefault>(ctx, in, first, n, prefix, out); break;
+      case 1: launch_tile_cfg<TILE_LEAF, false, TileV1>(ctx, in, 0, n, nullptr, out); break;
+      case 2: launch_tile_cfg<TILE_LEAF, false, TileV2>(ctx, in, 0, n, nullptr, out); break;
+      case 3: launch_tile_cfg<TILE_LEAF, false, TileV3>(ctx, in, 0, n, nullptr, out); break;
+      case 4: launch_tile_cfg<TILE_LEAF, false, TileV4>(ctx, in, 0, n, nullptr, out); break;
+      case 5: launch_tile_cfg<TILE_LEAF, false, TileV5>(ctx, in, 0, n, nullptr, out); break;
+      default: launch_tile_cfg<TILE_LEAF, false, TileDefault>(ctx, in, 0, n, nullptr, out); break;
     }
   }
-  LAUNCHED();
-  if (LEAF) {
-    CK(cudaEventRecord(ctx->leaf_events[2 * ctx->leaf_launches + 1], ctx->stream));
-    ++ctx->leaf_launches;
-    ctx->leaf_parents += n;
-  }
+  CK(cudaEventRecord(ctx->leaf_events[2 * ctx->leaf_launches + 1], ctx->stream));
+  ++ctx->leaf_launches;
+  ctx->leaf_parents += n;
+}
+
+/* K1: children of records [first, first + n) of `in`, at the offsets of `prefix` (count_and_scan) */
+void launch_expand(pabi_cuda_ctx* ctx, bool multi, Frontier in, size_t first, size_t n, const u64* prefix, Frontier children) {
+  const TileOut out{children, nullptr, nullptr, nullptr, nullptr};
+  if (multi) launch_tile_cfg<TILE_EXPAND, true, TileDefault>(ctx, in, first, n, prefix, out);
+  else launch_tile_cfg<TILE_EXPAND, false, TileDefault>(ctx, in, first, n, prefix, out);
+}
+
+/* K3: ordered move lists of records [0, n) at the offsets of `prefix`; the caller has checked the capacity */
+void launch_moves(pabi_cuda_ctx* ctx, const u64* rec, size_t stride, size_t n, const u64* prefix, u16* moves, u32* offsets) {
+  const TileOut out{Frontier{nullptr, nullptr, 0}, moves, offsets, nullptr, nullptr};
+  launch_tile_cfg<TILE_MOVES, false, TileDefault>(ctx, Frontier{const_cast<u64*>(rec), nullptr, stride}, 0, n, prefix, out);
 }
 
 /* Walks `remaining` plies below the n records of level `lv`, adding leaf counts
@@ -229,7 +233,7 @@ void descend(pabi_cuda_ctx* ctx, int lv, size_t n, int remaining, bool multi) {
     return;
   }
   if (remaining == 2) {
-    launch_tile<true>(ctx, multi, frontier_of(cur), 0, n, nullptr, Frontier{nullptr, nullptr, 0});
+    launch_leaf(ctx, multi, frontier_of(cur), n);
     /* the children are generated and counted inside the kernel */
     return;
   }
@@ -253,7 +257,7 @@ void descend(pabi_cuda_ctx* ctx, int lv, size_t n, int remaining, bool multi) {
       throw CudaFail{cudaErrorInvalidValue};
     }
     if (children) {
-      launch_tile<false>(ctx, multi, frontier_of(cur), start, end - start, cur.prefix, frontier_of(next));
+      launch_expand(ctx, multi, frontier_of(cur), start, end - start, cur.prefix, frontier_of(next));
       descend(ctx, lv + 1, children, remaining - 1, multi);
     }
     start = end;
@@ -348,7 +352,7 @@ int perft_impl(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, int d
           throw CudaFail{cudaErrorInvalidValue};
         }
         alloc_level(ctx, next, ctx->capacity);
-        if (children) launch_tile<false>(ctx, multi, frontier_of(cur), 0, cnt, cur.prefix, frontier_of(next));
+        if (children) launch_expand(ctx, multi, frontier_of(cur), 0, cnt, cur.prefix, frontier_of(next));
         ctx->interior += cnt;
         cnt = children, ++lv, --remaining;
       }
@@ -419,7 +423,6 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     CK(cudaFuncSetAttribute(k_count_accumulate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_in_check, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_make_moves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
-    CK(cudaFuncSetAttribute(k_emit_moves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     if (const char* v = std::getenv("PABI_TILE_VARIANT")) {
       ctx->tile_variant = std::atoi(v);
       if (ctx->tile_variant < 0 || ctx->tile_variant >= TILE_VARIANTS) ctx->tile_variant = 0;
@@ -580,10 +583,14 @@ int pabi_cuda_generate_moves_device(pabi_cuda_ctx* ctx, const uint64_t* device_r
     timer.begin_device();
     if (n) {
       count_and_scan(ctx, device_records, stride, 0, n, counts, prefix);
-      k_emit_moves<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(
-          ctx->dt, device_records, stride, n, prefix, device_moves, device_moves ? moves_cap : 0, device_offsets);
-      LAUNCHED();
       CK(cudaMemcpyAsync(ctx->h_result, prefix + n, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      if (device_moves && ctx->h_result[0] <= moves_cap) {
+        launch_moves(ctx, device_records, stride, n, prefix, device_moves, device_offsets);
+      } else {
+        k_prefix_to_offsets<<<grid_for(ctx, n + 1, 256, 8), 256, 0, ctx->stream>>>(prefix, n, device_offsets);
+        LAUNCHED();
+      }
     } else {
       CK(cudaMemsetAsync(device_offsets, 0, sizeof(u32), ctx->stream));
       ctx->h_result[0] = 0;
@@ -634,13 +641,17 @@ int pabi_cuda_generate_moves_batch(pabi_cuda_ctx* ctx, const pabi_position_t* po
     alloc_level(ctx, l0, n); /* counts/prefix of level 0 are the sizing arrays */
     timer.begin_device();
     count_and_scan(ctx, l0.rec, l0.cap, 0, n, l0.counts, l0.prefix);
-    k_emit_moves<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, l0.rec, l0.cap, n, l0.prefix,
-                                                                                            d_moves, moves_cap, d_offsets);
-    LAUNCHED();
+    CK(cudaMemcpyAsync(ctx->h_result, l0.prefix + n, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t total = (size_t)ctx->h_result[0];
+    if (total <= moves_cap && total) {
+      launch_moves(ctx, l0.rec, l0.cap, n, l0.prefix, d_moves, d_offsets);
+    } else {
+      k_prefix_to_offsets<<<grid_for(ctx, n + 1, 256, 8), 256, 0, ctx->stream>>>(l0.prefix, n, d_offsets);
+      LAUNCHED();
+    }
     timer.end_device();
     CK(cudaMemcpyAsync(offsets, d_offsets, (n + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    const size_t total = offsets[n];
     if (total <= moves_cap && total)
       CK(cudaMemcpyAsync(moves, d_moves, total * sizeof(u16), cudaMemcpyDeviceToHost, ctx->stream));
     timer.finish(timing, 64 * n + 4 * (n + 1) + 2 * total);
@@ -671,9 +682,7 @@ int pabi_cuda_expand_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions,
     u32* d_offsets = (u32*)ensure(ctx, 1, (n + 1) * sizeof(u32));
     timer.begin_device();
     count_and_scan(ctx, l0.rec, l0.cap, 0, n, l0.counts, l0.prefix);
-    /* offsets = low 32 bits of the prefix: reuse k_emit_moves with no move buffer */
-    k_emit_moves<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, l0.rec, l0.cap, n, l0.prefix,
-                                                                                            nullptr, 0, d_offsets);
+    k_prefix_to_offsets<<<grid_for(ctx, n + 1, 256, 8), 256, 0, ctx->stream>>>(l0.prefix, n, d_offsets);
     LAUNCHED();
     CK(cudaMemcpyAsync(offsets, d_offsets, (n + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -688,7 +697,7 @@ int pabi_cuda_expand_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions,
       if (total > ctx->capacity) return bad_arg(ctx, "children exceed the frontier capacity");
       Level& l1 = ctx->levels[1];
       alloc_level(ctx, l1, ctx->capacity);
-      launch_tile<false>(ctx, true, frontier_of(l0), 0, n, l0.prefix, frontier_of(l1));
+      launch_expand(ctx, true, frontier_of(l0), 0, n, l0.prefix, frontier_of(l1));
       PositionImage* d_out = (PositionImage*)ensure(ctx, 3, total * sizeof(PositionImage));
       k_unpack<<<grid_for(ctx, total, 256, 8), 256, 0, ctx->stream>>>(l1.rec, l1.cap, total, d_out);
       LAUNCHED();

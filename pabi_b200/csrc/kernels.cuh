@@ -2,11 +2,11 @@
  * kernels.cuh -- sm_100a kernels of the perft / move-generation path.
  *
  * K0  stage_tables        (device fn) 50 KB table image -> shared memory, once per block
- * K1  k_expand            one breadth-first ply: parents (SoA, HBM) -> children (SoA, HBM)
- * K2  k_leaf2             last two plies fused: parents -> children in shared memory ->
+ * K1  k_tile<TILE_EXPAND> one breadth-first ply: parents (SoA, HBM) -> children (SoA, HBM)
+ * K2  k_tile<TILE_LEAF>   last two plies fused: parents -> children in shared memory ->
  *                         count-only move generation per child, nothing written to HBM
  *     k_count             generate_moves().len() per record (perft depth 1, sizing pass of K1/K3)
- * K3  k_emit_moves        ordered u16 move lists at CSR offsets
+ * K3  k_tile<TILE_MOVES>  ordered u16 move lists at CSR offsets (same tile pipeline, coalesced stores)
  * K4  k_scan_*            exclusive prefix sum u32 -> u64 (reduce / spine / down-sweep)
  * K5  per-root accumulation, fused into k_leaf2 / k_count_accumulate
  *
@@ -155,24 +155,10 @@ k_make_moves(DeviceTables dt, const u64* __restrict__ rec, size_t stride, size_t
   }
 }
 
-/* K3: ordered move lists.  moves[prefix[i] - prefix[0] ...] in generate_moves order. */
-__global__ void __launch_bounds__(FLAT_THREADS)
-k_emit_moves(DeviceTables dt, const u64* __restrict__ rec, size_t stride, size_t n, const u64* __restrict__ prefix,
-             u16* __restrict__ moves, size_t moves_cap, u32* __restrict__ offsets) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  SharedTables* st = reinterpret_cast<SharedTables*>(smem);
-  stage_tables(st, dt.image);
-  const Tables tb{st, dt.g};
-  for (size_t i = (size_t)blockIdx.x * FLAT_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * FLAT_THREADS) {
-    const u64 base = prefix[i];
-    if (offsets) {
-      offsets[i] = (u32)base;
-      if (i + 1 == n) offsets[n] = (u32)prefix[n];
-    }
-    if (prefix[i + 1] > moves_cap) continue;
-    u16* dst = moves + base;
-    generate_moves(load_pos(rec, stride, i), tb, [&](int from, int to, int promo, int) { *dst++ = pack_move(from, to, promo); });
-  }
+/* CSR offsets (u32) from the u64 prefix */
+__global__ void k_prefix_to_offsets(const u64* __restrict__ prefix, size_t n, u32* __restrict__ offsets) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (size_t)gridDim.x * blockDim.x)
+    offsets[i] = (u32)(prefix[i] - prefix[0]);
 }
 
 /* ---- AoS (pabi_position_t, 112 B) <-> SoA record conversion -------------- */
@@ -366,11 +352,28 @@ __device__ __forceinline__ Pos tile_parent(const TileShared<CFG>& sh, int k) {
   return q;
 }
 
-template <bool LEAF, bool MULTI_ROOT, class CFG>
+enum TileMode {
+  TILE_LEAF,   /* K2: count the children, write nothing */
+  TILE_EXPAND, /* K1: write the children as SoA records */
+  TILE_MOVES   /* K3: write the moves themselves (u16, CSR) */
+};
+
+struct TileOut {
+  Frontier children;                /* TILE_EXPAND */
+  u16* moves;                       /* TILE_MOVES: moves[prefix[i] - prefix[first] ...] */
+  u32* offsets;                     /* TILE_MOVES: offsets[i] = prefix[first + i] - prefix[first] (n + 1 entries) */
+  unsigned long long* nodes;        /* TILE_LEAF: per-root (or single) leaf counts */
+  unsigned long long* visited;      /* TILE_LEAF statistics: children generated */
+};
+
+/* In TILE_EXPAND / TILE_MOVES the per-parent counts come from the global scan (`prefix`, built by
+ * k_count + k_scan_*), which also fixes where the tile's output starts; in TILE_LEAF they are
+ * computed here and scanned within the block. */
+template <TileMode MODE, bool MULTI_ROOT, class CFG>
 __global__ void __launch_bounds__(CFG::THREADS, CFG::MIN_BLOCKS)
-k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restrict__ prefix, Frontier out,
-       unsigned long long* __restrict__ nodes, unsigned long long* __restrict__ visited) {
+k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restrict__ prefix, TileOut out) {
   constexpr int THREADS = CFG::THREADS, PARENTS = CFG::PARENTS, POOL = CFG::POOL;
+  constexpr bool LEAF = MODE == TILE_LEAF;
   extern __shared__ __align__(16) unsigned char smem[];
   TileShared<CFG>& sh = *reinterpret_cast<TileShared<CFG>*>(smem);
   stage_tables(&sh.tables, dt.image);
@@ -382,10 +385,11 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
   for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const size_t i = tile * PARENTS + tid;
     const bool valid = tid < PARENTS && i < n;
-    u32 cnt = 0;
+    u32 cnt = 0, off = 0, total;
+    u64 out_base = 0; /* global index of this tile's first child / move */
     if (valid) {
       Pos p = load_pos(in.rec, in.stride, first + i);
-      cnt = count_moves(p, tb);
+      if (LEAF) cnt = count_moves(p, tb);
       /* K2 keeps the parent with BLACK to move (mirrored if necessary): every child is then "white
        * to move", which is what count_moves_white wants, and the mover's colour is a constant */
       if (LEAF && meta_stm(p.meta) == 0) p = mirror(p);
@@ -393,12 +397,27 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
       sh.parents[3][tid] = p.bishops, sh.parents[4][tid] = p.rooks, sh.parents[5][tid] = p.queens;
       sh.parents[6][tid] = p.kings, sh.parents[7][tid] = p.meta;
     }
-    if (LEAF && MULTI_ROOT && tid < PARENTS) sh.parent_nodes[tid] = 0;
-    u32 total;
-    const u32 off = block_exclusive_scan<THREADS>(cnt, sh.warp_sums, total);
-    if (LEAF && tid == 0 && total) atomicAdd(visited, (unsigned long long)total); /* statistics: positions at the last ply but one */
-    /* global index of this tile's first child (K1); prefix comes from the same count */
-    const u64 child_base = LEAF ? 0 : prefix[first + tile * PARENTS] - prefix[first];
+    if (LEAF) {
+      if (MULTI_ROOT && tid < PARENTS) sh.parent_nodes[tid] = 0;
+      off = block_exclusive_scan<THREADS>(cnt, sh.warp_sums, total);
+      if (tid == 0 && total) atomicAdd(out.visited, (unsigned long long)total); /* statistics: positions at the last ply but one */
+    } else {
+      const size_t tile_first = first + tile * PARENTS;
+      const size_t tile_end = first + min((tile + 1) * (size_t)PARENTS, n);
+      const u64 tile_prefix = prefix[tile_first];
+      out_base = tile_prefix - prefix[first];
+      total = (u32)(prefix[tile_end] - tile_prefix);
+      if (valid) {
+        const u64 mine = prefix[first + i];
+        off = (u32)(mine - tile_prefix);
+        cnt = (u32)(prefix[first + i + 1] - mine);
+        if (MODE == TILE_MOVES) {
+          out.offsets[i] = (u32)(mine - prefix[first]);
+          if (i + 1 == n) out.offsets[n] = (u32)(prefix[first + n] - prefix[first]);
+        }
+      }
+      __syncthreads(); /* the parents are in shared memory */
+    }
 
     for (u32 w = 0; w < total; w += POOL) {
       if (cnt && off < w + POOL && off + cnt > w) {
@@ -413,6 +432,10 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
       const u32 end = min(total - w, (u32)POOL);
       for (u32 c = tid; c < end; c += THREADS) {
         const u32 e = sh.pool[c];
+        if (MODE == TILE_MOVES) {
+          out.moves[out_base + w + c] = (u16)e;
+          continue;
+        }
         const int parent = (e >> 16) & 0xFFF;
         Pos q = tile_parent(sh, parent);
         if (LEAF) {
@@ -423,19 +446,19 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
           else acc += k;
         } else {
           make_move(q, tb, (u16)(e & 0xFFFF));
-          const size_t o = (size_t)(child_base + w + c);
-          store_pos(out.rec, out.stride, o, q);
-          if (MULTI_ROOT) out.roots[o] = in.roots[first + tile * PARENTS + parent];
+          const size_t o = (size_t)(out_base + w + c);
+          store_pos(out.children.rec, out.children.stride, o, q);
+          if (MULTI_ROOT) out.children.roots[o] = in.roots[first + tile * PARENTS + parent];
         }
       }
       __syncthreads();
     }
     if (LEAF && MULTI_ROOT) {
-      if (valid && sh.parent_nodes[tid]) atomicAdd(nodes + in.roots[first + i], (unsigned long long)sh.parent_nodes[tid]);
+      if (valid && sh.parent_nodes[tid]) atomicAdd(out.nodes + in.roots[first + i], (unsigned long long)sh.parent_nodes[tid]);
       __syncthreads();
     }
   }
-  if (LEAF && !MULTI_ROOT) block_add_u64<THREADS>(acc, sh.red, nodes);
+  if (LEAF && !MULTI_ROOT) block_add_u64<THREADS>(acc, sh.red, out.nodes);
 }
 
 } /* namespace pabi */
