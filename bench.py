@@ -207,10 +207,15 @@ def run_gpu(args) -> None:
         # children would be written and read back (128 B each).
         leaf_bytes = 64 * leaf_parents + 128 * leaf_children
         achieved = leaf_bytes / (leaf_ms * 1e-3) / 1e9 if leaf_ms else 0.0
-        traffic = None
+        # DRAM traffic of the leaf kernel from the committed ncu --set full capture (profiles/): the kernel only
+        # reads its parents, so the capture's bytes per parent scale to this run's launch size
+        traffic = traffic_note = None
         prof = ROOT / "profiles" / "leaf_kernel_traffic.json"
-        if prof.exists():
-            traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+        if prof.exists() and leaf_launches:
+            t = json.loads(prof.read_text())
+            traffic = t["dram_bytes_per_parent"] * leaf_parents / leaf_launches
+            traffic_note = (f"{t['dram_bytes_per_parent']:.1f} B/parent (dram__bytes_read+write of the ncu capture, "
+                            f"{t['parents_in_capture']} parents) x {leaf_parents // leaf_launches} parents per launch")
         line = {
             "metric": METRIC, "value": nodes_total / (device_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": device_ms_max / args.steps,
@@ -226,7 +231,7 @@ def run_gpu(args) -> None:
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_tile<LEAF=true> (fused last two plies)", "achieved": achieved,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                         "peak_source": peaks["source"], "traffic": traffic,
+                         "peak_source": peaks["source"], "traffic": traffic, "traffic_note": traffic_note,
                          "algorithmic_bytes_per_launch": leaf_bytes / max(1, leaf_launches),
                          "avg_launch_ms": leaf_ms / max(1, leaf_launches), "launches": leaf_launches,
                          "share_of_step": leaf_ms / device_ms if device_ms else None,

@@ -139,12 +139,14 @@ constexpr size_t FLAT_SMEM = sizeof(SharedTables);
 
 /* Tile-kernel geometries.  Variant 0 is the default; the others exist so that the
  * choice can be re-measured on the device (environment variable PABI_TILE_VARIANT). */
-using TileDefault = TileConfig<1024, 1024, 16384, 1>; /* 64 registers/thread, 32 warps per SM */
-using TileV1 = TileConfig<256, 256, 8192, 2>;
-using TileV2 = TileConfig<512, 512, 6144, 2>;
-using TileV3 = TileConfig<768, 768, 12288, 1>;
-using TileV4 = TileConfig<1024, 512, 16384, 1>;
-using TileV5 = TileConfig<1024, 1024, 24576, 1>;
+/* 1024 threads (64 registers each, 32 warps per SM) in four independent 256-thread groups that share one
+ * table image: while one group scans / generates, the others count */
+using TileDefault = TileConfig<1024, 256, 6144, 1, 4>;
+using TileV1 = TileConfig<1024, 512, 8192, 1, 2>;
+using TileV2 = TileConfig<1024, 1024, 16384, 1, 1>;
+using TileV3 = TileConfig<1024, 256, 5120, 1, 4>;
+using TileV4 = TileConfig<1024, 128, 3072, 1, 8>;
+using TileV5 = TileConfig<768, 256, 6144, 1, 3>;
 constexpr int TILE_VARIANTS = 6;
 
 /* counts[0..n) of records [first, first+n) of `l`, then prefix[0..n] */

@@ -42,9 +42,21 @@ struct Frontier {
 };
 
 /* ---- block-wide helpers -------------------------------------------------- */
-template <int THREADS>
-__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* warp_sums /* [THREADS/32 + 1] */, u32& total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+/* Barrier over one thread group of a block (bar.sync with an id and a thread count): groups of a
+ * block synchronise independently, so one group's scan/generate phase overlaps the other's
+ * counting phase while both share a single copy of the tables in shared memory. */
+template <int GROUP_THREADS>
+__device__ __forceinline__ void group_sync(int group) {
+  if (GROUP_THREADS == 0) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(GROUP_THREADS) : "memory");
+}
+
+/* Exclusive scan over the THREADS threads of one group (tid = index inside the group). */
+template <int THREADS, int GROUP_THREADS = 0>
+__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* warp_sums /* [THREADS/32 + 1] */, u32& total, int tid_in = -1,
+                                                    int group = 0) {
+  const int tid = tid_in >= 0 ? tid_in : (int)threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
   u32 inc = v;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -52,7 +64,7 @@ __device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* warp_sums /* [TH
     if (lane >= d) inc += o;
   }
   if (lane == 31) warp_sums[warp] = inc;
-  __syncthreads();
+  group_sync<GROUP_THREADS>(group);
   if (warp == 0) {
     constexpr int NW = THREADS / 32;
     u32 w = lane < NW ? warp_sums[lane] : 0;
@@ -65,10 +77,10 @@ __device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* warp_sums /* [TH
     if (lane < NW) warp_sums[lane] = winc - w;
     if (lane == NW - 1) warp_sums[NW] = winc;
   }
-  __syncthreads();
+  group_sync<GROUP_THREADS>(group);
   total = warp_sums[THREADS / 32];
   const u32 r = warp_sums[warp] + inc - v;
-  __syncthreads(); /* warp_sums may be reused by the caller's next scan */
+  group_sync<GROUP_THREADS>(group); /* warp_sums may be reused by the caller's next scan */
   return r;
 }
 
@@ -328,24 +340,33 @@ __global__ void k_chunk_end(const u64* __restrict__ prefix, size_t start, size_t
  * The geometry (threads, parents per tile, pool entries, blocks per SM) is a
  * template parameter so that variants can be timed against each other on the
  * device (PABI_TILE_VARIANT, see engine.cu). */
-template <int THREADS_, int PARENTS_, int POOL_, int MIN_BLOCKS_>
+/* THREADS threads per block in GROUPS independent groups; each group works on tiles of PARENTS
+ * parents with its own pool of POOL entries. */
+template <int THREADS_, int PARENTS_, int POOL_, int MIN_BLOCKS_, int GROUPS_ = 1>
 struct TileConfig {
-  static constexpr int THREADS = THREADS_, PARENTS = PARENTS_, POOL = POOL_, MIN_BLOCKS = MIN_BLOCKS_;
-  static_assert(PARENTS_ <= THREADS_ && PARENTS_ <= 4096 && POOL_ >= 256, "a tile's parents need a thread each; the pool must hold one move list");
+  static constexpr int THREADS = THREADS_, PARENTS = PARENTS_, POOL = POOL_, MIN_BLOCKS = MIN_BLOCKS_, GROUPS = GROUPS_;
+  static constexpr int GROUP_THREADS = THREADS_ / GROUPS_;
+  static_assert(THREADS_ % (32 * GROUPS_) == 0 && GROUPS_ <= 15, "groups are whole warps; barrier ids 1..15");
+  static_assert(PARENTS_ <= GROUP_THREADS && PARENTS_ <= 4096 && POOL_ >= 256, "a tile's parents need a thread each; the pool must hold one move list");
+};
+
+template <class CFG>
+struct TileGroupShared {
+  u64 parents[POS_WORDS][CFG::PARENTS];
+  u32 pool[CFG::POOL];
+  u32 parent_nodes[CFG::PARENTS]; /* K2, multi-root: nodes below each parent */
+  u32 warp_sums[CFG::GROUP_THREADS / 32 + 1];
 };
 
 template <class CFG>
 struct TileShared {
   SharedTables tables;
-  u64 parents[POS_WORDS][CFG::PARENTS];
-  u32 pool[CFG::POOL];
-  u32 parent_nodes[CFG::PARENTS]; /* K2, multi-root: nodes below each parent */
-  u32 warp_sums[CFG::THREADS / 32 + 1];
+  TileGroupShared<CFG> group[CFG::GROUPS];
   u64 red[CFG::THREADS / 32];
 };
 
 template <class CFG>
-__device__ __forceinline__ Pos tile_parent(const TileShared<CFG>& sh, int k) {
+__device__ __forceinline__ Pos tile_parent(const TileGroupShared<CFG>& sh, int k) {
   Pos q;
   q.white = sh.parents[0][k], q.pawns = sh.parents[1][k], q.knights = sh.parents[2][k], q.bishops = sh.parents[3][k];
   q.rooks = sh.parents[4][k], q.queens = sh.parents[5][k], q.kings = sh.parents[6][k], q.meta = sh.parents[7][k];
@@ -372,17 +393,20 @@ struct TileOut {
 template <TileMode MODE, bool MULTI_ROOT, class CFG>
 __global__ void __launch_bounds__(CFG::THREADS, CFG::MIN_BLOCKS)
 k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restrict__ prefix, TileOut out) {
-  constexpr int THREADS = CFG::THREADS, PARENTS = CFG::PARENTS, POOL = CFG::POOL;
+  constexpr int PARENTS = CFG::PARENTS, POOL = CFG::POOL, GROUPS = CFG::GROUPS, GT = CFG::GROUP_THREADS;
+  constexpr int SYNC = GROUPS == 1 ? 0 : GT; /* 0: plain __syncthreads */
   constexpr bool LEAF = MODE == TILE_LEAF;
   extern __shared__ __align__(16) unsigned char smem[];
-  TileShared<CFG>& sh = *reinterpret_cast<TileShared<CFG>*>(smem);
-  stage_tables(&sh.tables, dt.image);
-  const Tables tb{&sh.tables, dt.g};
-  const int tid = threadIdx.x;
+  TileShared<CFG>& block = *reinterpret_cast<TileShared<CFG>*>(smem);
+  stage_tables(&block.tables, dt.image);
+  const Tables tb{&block.tables, dt.g};
+  const int group = GROUPS == 1 ? 0 : threadIdx.x / GT;
+  const int tid = GROUPS == 1 ? threadIdx.x : threadIdx.x % GT;
+  TileGroupShared<CFG>& sh = block.group[group];
   u64 acc = 0;
   const size_t n_tiles = (n + PARENTS - 1) / PARENTS;
 
-  for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (size_t tile = (size_t)blockIdx.x * GROUPS + group; tile < n_tiles; tile += (size_t)gridDim.x * GROUPS) {
     const size_t i = tile * PARENTS + tid;
     const bool valid = tid < PARENTS && i < n;
     u32 cnt = 0, off = 0, total;
@@ -399,7 +423,7 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
     }
     if (LEAF) {
       if (MULTI_ROOT && tid < PARENTS) sh.parent_nodes[tid] = 0;
-      off = block_exclusive_scan<THREADS>(cnt, sh.warp_sums, total);
+      off = block_exclusive_scan<GT, SYNC>(cnt, sh.warp_sums, total, tid, group);
       if (tid == 0 && total) atomicAdd(out.visited, (unsigned long long)total); /* statistics: positions at the last ply but one */
     } else {
       const size_t tile_first = first + tile * PARENTS;
@@ -416,7 +440,7 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
           if (i + 1 == n) out.offsets[n] = (u32)(prefix[first + n] - prefix[first]);
         }
       }
-      __syncthreads(); /* the parents are in shared memory */
+      group_sync<SYNC>(group); /* the parents are in shared memory */
     }
 
     for (u32 w = 0; w < total; w += POOL) {
@@ -428,9 +452,9 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
           if (slot < (u32)POOL) sh.pool[slot] = ((u32)kind << 28) | ((u32)tid << 16) | pack_move(from, to, promo);
         });
       }
-      __syncthreads();
+      group_sync<SYNC>(group);
       const u32 end = min(total - w, (u32)POOL);
-      for (u32 c = tid; c < end; c += THREADS) {
+      for (u32 c = tid; c < end; c += GT) {
         const u32 e = sh.pool[c];
         if (MODE == TILE_MOVES) {
           out.moves[out_base + w + c] = (u16)e;
@@ -451,14 +475,14 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
           if (MULTI_ROOT) out.children.roots[o] = in.roots[first + tile * PARENTS + parent];
         }
       }
-      __syncthreads();
+      group_sync<SYNC>(group);
     }
     if (LEAF && MULTI_ROOT) {
       if (valid && sh.parent_nodes[tid]) atomicAdd(out.nodes + in.roots[first + i], (unsigned long long)sh.parent_nodes[tid]);
-      __syncthreads();
+      group_sync<SYNC>(group);
     }
   }
-  if (LEAF && !MULTI_ROOT) block_add_u64<THREADS>(acc, sh.red, out.nodes);
+  if (LEAF && !MULTI_ROOT) block_add_u64<CFG::THREADS>(acc, block.red, out.nodes);
 }
 
 } /* namespace pabi */
