@@ -156,3 +156,15 @@ def test_random_playout_positions_match_the_oracle():
             assert bad == 0, where
             total += visited
     assert total > 20000
+
+
+def test_published_perft_values_through_the_device_logic():
+    """tests/published_perft.py: independent values, through the leaf-kernel code path compiled for the host."""
+    from published_perft import MAX_MOVES_FEN, PUBLISHED
+    for fen, depth, nodes in PUBLISHED:
+        if nodes <= 4_000_000:
+            p = oracle.parse(fen)
+            assert hostcheck.lib().hostcheck_perft(C.byref(p), depth) == nodes, fen
+    p = oracle.parse(MAX_MOVES_FEN)
+    assert hostcheck.lib().hostcheck_count_moves(C.byref(p)) == 218
+    assert gen(p) == oracle.generate_moves(p)
