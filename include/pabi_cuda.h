@@ -116,6 +116,10 @@ int pabi_cuda_count_moves_batch(pabi_cuda_ctx* ctx, const pabi_position_t* posit
 /* Position::in_check(), src/chess/position.rs:735-746, for n positions */
 int pabi_cuda_in_check_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, size_t n,
                              uint8_t* in_check /* [n] */, pabi_timing_t* timing);
+/* Position::attack_info(), src/chess/position.rs:285-292 -> AttackInfo (src/chess/attacks.rs:89-97) for n
+ * positions: out[5*i .. 5*i+5) = attacks, checkers, pins, xrays, safe_king_squares of position i. */
+int pabi_cuda_attack_info_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, size_t n,
+                                uint64_t* out /* [5 * n] */, pabi_timing_t* timing);
 /* Position::make_move(&Move), src/chess/position.rs:414-433: out[i] = positions[i] after moves[i]
  * (moves must be legal; the hash field of every device-produced position is 0: the reference's
  * Zobrist keys are build-random, generated.rs:15-16, so hash values cannot be reproduced). */

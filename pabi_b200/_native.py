@@ -76,7 +76,7 @@ EXPORTS = (
     "pabi_move_from_uci", "pabi_move_to_uci", "pabi_cuda_create", "pabi_cuda_destroy", "pabi_cuda_last_error",
     "pabi_cuda_device", "pabi_cuda_perft", "pabi_cuda_perft_batch", "pabi_cuda_perft_shard", "pabi_cuda_perft_divide",
     "pabi_cuda_generate_moves_batch", "pabi_cuda_count_moves_batch", "pabi_cuda_in_check_batch",
-    "pabi_cuda_make_moves_batch", "pabi_cuda_expand_batch", "pabi_cuda_pack_records",
+    "pabi_cuda_attack_info_batch", "pabi_cuda_make_moves_batch", "pabi_cuda_expand_batch", "pabi_cuda_pack_records",
     "pabi_cuda_generate_moves_device",
 )
 
@@ -120,6 +120,7 @@ def lib() -> C.CDLL:
     L.pabi_cuda_generate_moves_batch.argtypes = [vp, vp, sz, vp, vp, sz, T]
     L.pabi_cuda_count_moves_batch.argtypes = [vp, vp, sz, vp, T]
     L.pabi_cuda_in_check_batch.argtypes = [vp, vp, sz, vp, T]
+    L.pabi_cuda_attack_info_batch.argtypes = [vp, vp, sz, vp, T]
     L.pabi_cuda_make_moves_batch.argtypes = [vp, vp, vp, sz, vp, T]
     L.pabi_cuda_expand_batch.argtypes = [vp, vp, sz, vp, vp, sz, T]
     L.pabi_cuda_pack_records.argtypes = [vp, vp, sz, vp, sz]

@@ -179,6 +179,15 @@ class Engine:
         self.last_timing = t
         return out.astype(bool)
 
+    def attack_info_batch(self, positions) -> np.ndarray:
+        """AttackInfo (src/chess/attacks.rs:89-97) per position: columns attacks, checkers, pins, xrays,
+        safe_king_squares."""
+        arr = _as_array(positions)
+        out, t = np.zeros((len(arr), 5), dtype=np.uint64), Timing()
+        self._check(_native.lib().pabi_cuda_attack_info_batch(self._ctx, arr.ctypes.data, len(arr), out.ctypes.data, C.byref(t)))
+        self.last_timing = t
+        return out
+
     def make_moves_batch(self, positions, moves: Sequence[int]) -> np.ndarray:
         arr = _as_array(positions)
         mv = np.ascontiguousarray(np.asarray(moves, dtype=np.uint16))
@@ -286,6 +295,11 @@ class Position:
         hash_ = self.raw.hash
         C.memmove(C.byref(self.raw), out.ctypes.data, 112)
         self.raw.hash = hash_
+
+    def attack_info(self, engine: Optional[Engine] = None) -> dict:
+        """`Position::attack_info()` (position.rs:285-292)."""
+        row = (engine or default_engine()).attack_info_batch([self])[0]
+        return dict(zip(("attacks", "checkers", "pins", "xrays", "safe_king_squares"), (int(x) for x in row)))
 
     def in_check(self, engine: Optional[Engine] = None) -> bool:
         return bool((engine or default_engine()).in_check_batch([self])[0])

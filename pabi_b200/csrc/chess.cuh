@@ -301,6 +301,59 @@ PB_HD void analyze(const Pos& p, const TB& tb, Analysis& a) {
   }
 }
 
+/* AttackInfo exactly as the reference publishes it (attacks.rs:89-200, Position::attack_info
+ * position.rs:285-292): `attacks` with the full occupancy (sliders do NOT look through the king),
+ * `xrays` included, `safe_king_squares` with the checking sliders' rays extended through the king.
+ * Move generation uses analyze() above; this is the API-level picture the reference's tests pin
+ * (attacks.rs:555-695). */
+struct AttackInfoOut {
+  u64 attacks, checkers, pins, xrays, safe_king_squares;
+};
+template <class TB>
+PB_HD AttackInfoOut attack_info(const Pos& p, const TB& tb) {
+  const int us = meta_stm(p.meta), them = us ^ 1;
+  const u64 occ = p.pawns | p.knights | p.bishops | p.rooks | p.queens | p.kings;
+  const u64 our = us == 0 ? p.white : occ & ~p.white;
+  const u64 their = occ ^ our;
+  const u64 king_bb = p.kings & our;
+  const int king = lsb(king_bb);
+  const u64 occ_nk = occ ^ king_bb;
+  AttackInfoOut r;
+  r.attacks = tb.king(lsb(p.kings & their)) | pawn_attacks(p.pawns & their, them);
+  r.checkers = pawn_attacks(king_bb, us) & p.pawns & their;
+  r.pins = r.xrays = 0;
+  u64 safe = tb.king(king) & ~our;
+  for (u64 b = p.knights & their; b; b &= b - 1) {
+    const u64 t = tb.knight(lsb(b));
+    r.attacks |= t;
+    if (t & king_bb) r.checkers |= b & (0 - b);
+  }
+  /* queens, bishops, rooks (attacks.rs:138-197); the blocker test uses the ray towards the king */
+  for (int diag = 0; diag < 2; diag++) {
+    for (u64 b = (diag ? p.bishops | p.queens : p.rooks | p.queens) & their; b; b &= b - 1) {
+      const int sq = lsb(b);
+      const u64 t = diag ? tb.bishop(sq, occ) : tb.rook(sq, occ);
+      r.attacks |= t;
+      if (t & king_bb) {
+        r.checkers |= b & (0 - b);
+        safe &= ~(diag ? tb.bishop(sq, occ_nk) : tb.rook(sq, occ_nk));
+        continue;
+      }
+      /* bishop_ray / rook_ray (attacks.rs:58-64): the ray only when aligned the slider's way; a queen takes part in
+       * both passes, and is aligned with the king in at most one of them */
+      const bool same_line = ((sq ^ king) & 7) == 0 || ((sq ^ king) & 56) == 0;
+      const u64 ray = (diag ? !same_line : same_line) ? tb.ray(sq, king) : 0;
+      const u64 blockers = (ray & occ) & ~(b & (0 - b));
+      if (blockers && (blockers & (blockers - 1)) == 0) {
+        if (blockers & our) r.pins |= blockers;
+        else r.xrays |= blockers;
+      }
+    }
+  }
+  r.safe_king_squares = safe & ~r.attacks;
+  return r;
+}
+
 /* position.rs:1226-1288 with the walk masks of attacks.rs:203-214.  Returns a
  * 2-bit set: bit 0 short, bit 1 long. */
 PB_HD int castle_moves(const Pos& p, const Analysis& a) {
@@ -663,9 +716,9 @@ PB_HD void make_move(Pos& p, const TB& tb, u16 mv) {
     } else {
       p.pawns |= tbit;
       /* :606-615: the en passant square is recorded only when an enemy pawn attacks it */
-      if ((from ^ to) == 16) {
-        const u64 skipped = bit((from + to) >> 1);
-        if (pawn_attacks(skipped, us) & p.pawns & ~our & ~fb) ep = (from + to) >> 1;
+      if ((from ^ to) == 16) { /* the pawns that attack the skipped square stand beside the pushed pawn */
+        const u64 beside = ((tbit & ~FILE_H) << 1) | ((tbit & ~FILE_A) >> 1);
+        if (beside & p.pawns & ~our) ep = (from + to) >> 1;
       }
     }
   } else if (p.kings & fb) { /* make_king_move, :622-698 */
@@ -726,9 +779,9 @@ PB_HD void make_move_kind(Pos& p, const TB& tb, u16 mv, int kind) {
       else p.knights |= tbit;
     } else {
       p.pawns |= tbit;
-      if ((from ^ to) == 16) {
-        const u64 their_pawns = p.pawns & (us == 0 ? ~white : white) & ~tbit;
-        if (pawn_attacks(bit((from + to) >> 1), us) & their_pawns) ep = (from + to) >> 1;
+      if ((from ^ to) == 16) { /* the pawns that attack the skipped square stand beside the pushed pawn */
+        const u64 beside = ((tbit & ~FILE_H) << 1) | ((tbit & ~FILE_A) >> 1);
+        if (beside & p.pawns & (us == 0 ? ~white : white)) ep = (from + to) >> 1;
       }
     }
   } else if (kind == KIND_KING) {

@@ -424,6 +424,7 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     CK(cudaFuncSetAttribute(k_count_accumulate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_count_accumulate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_in_check, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_attack_info, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_make_moves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     if (const char* v = std::getenv("PABI_TILE_VARIANT")) {
       ctx->tile_variant = std::atoi(v);
@@ -536,6 +537,31 @@ int pabi_cuda_in_check_batch(pabi_cuda_ctx* ctx, const pabi_position_t* position
     timer.end_device();
     CK(cudaMemcpyAsync(in_check, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
     timer.finish(timing, 65 * n);
+    return 0;
+  } catch (const CudaFail& f) {
+    return fail(ctx, f);
+  }
+}
+
+int pabi_cuda_attack_info_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, size_t n, uint64_t* out,
+                                pabi_timing_t* timing) {
+  if (!ctx || (n && (!positions || !out))) return bad_arg(ctx, "null argument");
+  try {
+    CK(cudaSetDevice(ctx->device));
+    CallTimer timer(ctx);
+    if (n == 0) {
+      timer.begin_device(), timer.end_device(), timer.finish(timing, 0);
+      return 0;
+    }
+    upload_roots(ctx, positions, n);
+    Level& l0 = ctx->levels[0];
+    u64* d_out = (u64*)ensure(ctx, 1, 5 * n * sizeof(u64));
+    timer.begin_device();
+    k_attack_info<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, l0.rec, l0.cap, n, d_out);
+    LAUNCHED();
+    timer.end_device();
+    CK(cudaMemcpyAsync(out, d_out, 5 * n * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    timer.finish(timing, 104 * n);
     return 0;
   } catch (const CudaFail& f) {
     return fail(ctx, f);

@@ -152,6 +152,20 @@ k_in_check(DeviceTables dt, const u64* __restrict__ rec, size_t stride, size_t n
   }
 }
 
+/* AttackInfo (attacks.rs:89-200): five bitboards per record */
+__global__ void __launch_bounds__(FLAT_THREADS)
+k_attack_info(DeviceTables dt, const u64* __restrict__ rec, size_t stride, size_t n, u64* __restrict__ out /* [n][5] */) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SharedTables* st = reinterpret_cast<SharedTables*>(smem);
+  stage_tables(st, dt.image);
+  const Tables tb{st, dt.g};
+  for (size_t i = (size_t)blockIdx.x * FLAT_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * FLAT_THREADS) {
+    const AttackInfoOut a = attack_info(load_pos(rec, stride, i), tb);
+    u64* o = out + 5 * i;
+    o[0] = a.attacks, o[1] = a.checkers, o[2] = a.pins, o[3] = a.xrays, o[4] = a.safe_king_squares;
+  }
+}
+
 /* out[i] = rec[i] after moves[i] (position.rs:414-433) */
 __global__ void __launch_bounds__(FLAT_THREADS)
 k_make_moves(DeviceTables dt, const u64* __restrict__ rec, size_t stride, size_t n, const u16* __restrict__ moves,

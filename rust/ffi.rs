@@ -68,6 +68,7 @@ extern "C" {
                                        t: *mut Timing) -> i32;
     pub fn pabi_cuda_in_check_batch(ctx: *mut Ctx, positions: *const RawPosition, n: usize, in_check: *mut u8,
                                     t: *mut Timing) -> i32;
+    pub fn pabi_cuda_attack_info_batch(ctx: *mut Ctx, positions: *const RawPosition, n: usize, out: *mut u64, t: *mut Timing) -> i32;
     pub fn pabi_cuda_make_moves_batch(ctx: *mut Ctx, positions: *const RawPosition, moves: *const u16, n: usize,
                                       out: *mut RawPosition, t: *mut Timing) -> i32;
     pub fn pabi_cuda_expand_batch(ctx: *mut Ctx, positions: *const RawPosition, n: usize, offsets: *mut u32,

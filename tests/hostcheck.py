@@ -26,6 +26,7 @@ def lib() -> C.CDLL:
         L.hostcheck_make_move.argtypes = [P, C.c_uint16]
         L.hostcheck_in_check.argtypes = [P]
         L.hostcheck_analysis.argtypes = [P, C.POINTER(C.c_uint64)]
+        L.hostcheck_attack_info.argtypes = [P, C.POINTER(C.c_uint64)]
         L.hostcheck_perft.restype = C.c_uint64
         L.hostcheck_perft.argtypes = [P, C.c_int]
         L.hostcheck_walk_compare.restype = C.c_uint64

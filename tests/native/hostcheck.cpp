@@ -46,6 +46,11 @@ void hostcheck_analysis(const pabi_position_t* p, uint64_t out[5]) {
   out[0] = a.attacks, out[1] = a.checkers, out[2] = a.pins, out[3] = a.safe_king, out[4] = a.block;
 }
 
+void hostcheck_attack_info(const pabi_position_t* p, uint64_t out[5]) {
+  const AttackInfoOut a = attack_info(pack_record(*p), host_tb());
+  out[0] = a.attacks, out[1] = a.checkers, out[2] = a.pins, out[3] = a.xrays, out[4] = a.safe_king_squares;
+}
+
 static uint64_t perft_rec(const Pos& p, const Tables& tb, int depth) {
   if (depth == 0) return 1;
   if (depth == 1) return count_moves(p, tb);

@@ -168,3 +168,26 @@ def test_published_perft_values_through_the_device_logic():
     p = oracle.parse(MAX_MOVES_FEN)
     assert hostcheck.lib().hostcheck_count_moves(C.byref(p)) == 218
     assert gen(p) == oracle.generate_moves(p)
+
+
+def test_attack_info_matches_the_reference_pictures_and_the_oracle(vectors):
+    """AttackInfo as the reference publishes it (attacks.rs:555-695 pictures), all five fields."""
+    def device_ai(p):
+        out = (C.c_uint64 * 5)()
+        hostcheck.lib().hostcheck_attack_info(C.byref(p), out)
+        return dict(zip(("attacks", "checkers", "pins", "xrays", "safe_king_squares"), out))
+    for case in vectors["attacks"]["attack_info"]:
+        got = device_ai(oracle.parse(case["fen"]))
+        for field, bits in case["fields"].items():
+            assert got[field] == int(bits), (case["source"], field)
+    start = oracle.starting()
+    n = 0
+    for g in range(120):
+        arr = oracle.random_playout(start, 0xA77AC0 + g, 160)
+        for i in range(len(arr)):
+            p = oracle.Position.from_buffer_copy(arr[i].tobytes())
+            want = oracle.attack_info(p)
+            got = device_ai(p)
+            assert all(got[f] == getattr(want, f) for f in got), oracle.to_fen(p)
+            n += 1
+    assert n > 8000

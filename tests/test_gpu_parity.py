@@ -160,6 +160,19 @@ def test_in_check(engine, playout_positions):
     assert got.tolist() == want
 
 
+def test_attack_info(pb, engine, vectors, playout_positions):
+    """AttackInfo pictures of attacks.rs:555-695 and the oracle on playout positions, five fields each."""
+    for case in vectors["attacks"]["attack_info"]:
+        got = fen_pos(pb, case["fen"]).attack_info(engine)
+        for field, bits in case["fields"].items():
+            assert got[field] == int(bits), (case["source"], field)
+    batch = np.ascontiguousarray(playout_positions[:6000])
+    got = engine.attack_info_batch(batch)
+    for i in range(len(batch)):
+        ai = oracle.attack_info(oracle.Position.from_buffer_copy(batch[i].tobytes()))
+        assert got[i].tolist() == [ai.attacks, ai.checkers, ai.pins, ai.xrays, ai.safe_king_squares]
+
+
 # ---- make_move: children of a ply, field for field (tests/chess.rs:474-531,580-620) ----
 
 def test_reference_make_move_vectors(pb, engine, vectors):
