@@ -151,19 +151,19 @@ class Engine:
         """CSR move lists: (offsets[n+1] u32, moves u16) in the reference's order."""
         arr = _as_array(positions)
         n = len(arr)
-        offsets = np.zeros(n + 1, dtype=np.uint32)
-        moves = np.zeros(max(64, 48 * n), dtype=np.uint16)
+        offsets = np.empty(n + 1, dtype=np.uint32)
+        moves = np.empty(max(256, 40 * n), dtype=np.uint16)  # ~28 moves per position on playout positions
         t = Timing()
         L = _native.lib()
         rc = L.pabi_cuda_generate_moves_batch(self._ctx, arr.ctypes.data, n, offsets.ctypes.data, moves.ctypes.data,
                                               len(moves), C.byref(t))
         if rc == -2:
-            moves = np.zeros(int(offsets[n]), dtype=np.uint16)
+            moves = np.empty(int(offsets[n]), dtype=np.uint16)
             rc = L.pabi_cuda_generate_moves_batch(self._ctx, arr.ctypes.data, n, offsets.ctypes.data, moves.ctypes.data,
                                                   len(moves), C.byref(t))
         self._check(rc)
         self.last_timing = t
-        return offsets, moves[: int(offsets[n])].copy()
+        return offsets, moves[: int(offsets[n])]
 
     def count_moves_batch(self, positions) -> np.ndarray:
         arr = _as_array(positions)
