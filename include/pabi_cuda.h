@@ -97,6 +97,12 @@ int pabi_cuda_perft_batch(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size
 int pabi_cuda_perft_shard(pabi_cuda_ctx* ctx, const pabi_position_t* root, uint8_t depth,
                           uint32_t split_ply, uint32_t shard_index, uint32_t shard_count,
                           uint64_t* nodes, pabi_timing_t* timing);
+/* Single-process multi-GPU perft: one context per device (pabi_cuda_create), one host thread per
+ * context inside the call, shard i of n_ctx on ctxs[i], host-side u64 sum.  per_ctx_ms (optional,
+ * [n_ctx]) receives each device's CUDA-event time.  (bench.py uses one process per GPU and
+ * torch.distributed instead; this is what a single Rust process would call.) */
+int pabi_cuda_perft_multi(pabi_cuda_ctx* const* ctxs, size_t n_ctx, const pabi_position_t* root, uint8_t depth,
+                          uint32_t split_ply, uint64_t* nodes, double* per_ctx_ms);
 /* perft "divide": the root's moves in generate_moves order with the node count
  * below each (the per-move breakdown `go perft` prints; engine/mod.rs:176-190). */
 int pabi_cuda_perft_divide(pabi_cuda_ctx* ctx, const pabi_position_t* root, uint8_t depth,

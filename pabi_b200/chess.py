@@ -214,6 +214,18 @@ class Engine:
         return offsets, children
 
 
+def perft_multi(engines: Sequence[Engine], position: "Position", depth: int, split_ply: int = 4) -> Tuple[int, List[float]]:
+    """perft over several contexts (normally one per GPU) from one process: `pabi_cuda_perft_multi`.
+    Returns (nodes, per-context device milliseconds)."""
+    n = len(engines)
+    ctxs = (C.c_void_p * n)(*[e._ctx for e in engines])
+    nodes, ms = C.c_uint64(), (C.c_double * n)()
+    rc = _native.lib().pabi_cuda_perft_multi(ctxs, n, C.byref(position.raw), depth, split_ply, C.byref(nodes), ms)
+    if rc != 0:
+        raise PabiCudaError(rc, "; ".join(_native.lib().pabi_cuda_last_error(e._ctx).decode() for e in engines))
+    return nodes.value, list(ms)
+
+
 _default_engine: Optional[Engine] = None
 
 

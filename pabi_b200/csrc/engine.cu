@@ -19,6 +19,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pabi_cuda.h"
@@ -491,6 +492,30 @@ int pabi_cuda_perft_shard(pabi_cuda_ctx* ctx, const pabi_position_t* root, uint8
   if (!ctx || !root || !nodes) return bad_arg(ctx, "null argument");
   if (shard_count == 0 || shard_index >= shard_count) return bad_arg(ctx, "shard_index must be < shard_count");
   return perft_impl(ctx, root, 1, depth, nodes, false, split_ply, shard_index, shard_count, timing);
+}
+
+int pabi_cuda_perft_multi(pabi_cuda_ctx* const* ctxs, size_t n_ctx, const pabi_position_t* root, uint8_t depth,
+                          uint32_t split_ply, uint64_t* nodes, double* per_ctx_ms) {
+  if (!ctxs || n_ctx == 0 || !root || !nodes) return -1;
+  for (size_t i = 0; i < n_ctx; i++)
+    if (!ctxs[i]) return -1;
+  std::vector<uint64_t> part(n_ctx, 0);
+  std::vector<int> rc(n_ctx, 0);
+  std::vector<pabi_timing_t> timing(n_ctx);
+  std::vector<std::thread> workers;
+  for (size_t i = 0; i < n_ctx; i++)
+    workers.emplace_back([&, i] {
+      rc[i] = pabi_cuda_perft_shard(ctxs[i], root, depth, split_ply, (uint32_t)i, (uint32_t)n_ctx, &part[i], &timing[i]);
+    });
+  for (std::thread& w : workers) w.join();
+  uint64_t total = 0;
+  for (size_t i = 0; i < n_ctx; i++) {
+    if (rc[i]) return rc[i];
+    total += part[i];
+    if (per_ctx_ms) per_ctx_ms[i] = timing[i].device_ms;
+  }
+  *nodes = total;
+  return 0;
 }
 
 int pabi_cuda_count_moves_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, size_t n, uint32_t* counts,

@@ -60,6 +60,8 @@ extern "C" {
                                  t: *mut Timing) -> i32;
     pub fn pabi_cuda_perft_shard(ctx: *mut Ctx, root: *const RawPosition, depth: u8, split_ply: u32, shard_index: u32,
                                  shard_count: u32, nodes: *mut u64, t: *mut Timing) -> i32;
+    pub fn pabi_cuda_perft_multi(ctxs: *const *mut Ctx, n_ctx: usize, root: *const RawPosition, depth: u8, split_ply: u32,
+                                 nodes: *mut u64, per_ctx_ms: *mut f64) -> i32;
     pub fn pabi_cuda_perft_divide(ctx: *mut Ctx, root: *const RawPosition, depth: u8, moves_out: *mut u16,
                                   nodes_out: *mut u64, n_moves: *mut u32, t: *mut Timing) -> i32;
     pub fn pabi_cuda_generate_moves_batch(ctx: *mut Ctx, positions: *const RawPosition, n: usize, offsets: *mut u32,

@@ -114,6 +114,20 @@ def test_shards_sum_to_the_whole(pb, engine):
             assert sum(engine.perft_shard(p, depth, split, i, count) for i in range(count)) == whole
 
 
+def test_perft_multi_contexts_in_one_process(pb, engine, small_engine):
+    """pabi_cuda_perft_multi: several contexts (here two on the same device, one of them with a tiny
+    frontier), one host thread each, host-side sum."""
+    import torch
+    p = pb.Position.from_fen(KIWIPETE)
+    nodes, ms = pb.perft_multi([engine, small_engine], p, 4, split_ply=2)
+    assert nodes == 4085603 and len(ms) == 2
+    if torch.cuda.device_count() >= 2:
+        other = pb.Engine(1)
+        nodes, _ = pb.perft_multi([engine, other], pb.Position.starting(), 6)
+        assert nodes == 119060324
+        other.close()
+
+
 def test_divide(pb, engine):
     p = pb.Position.from_fen(KIWIPETE)
     op = oracle.parse(KIWIPETE)
