@@ -138,6 +138,17 @@ int pabi_cuda_expand_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions,
                            uint32_t* offsets /* [n+1] */, pabi_position_t* children, size_t children_cap,
                            pabi_timing_t* timing);
 
+/* Seeded uniform-random playouts on the device: the position source of the datagen-style workload
+ * (the loop a src/datagen driver runs around Position::generate_moves / make_move,
+ * src/chess/position.rs:317-433; src/datagen itself is empty upstream).  Game g starts from starts[g];
+ * at each ply the move is moves[splitmix64(seeds[g]) % n] in generate_moves order; the position after
+ * every stride-th ply (ply 0 included) is written to out[g * per_game_cap + k] until there is no legal
+ * move, the halfmove clock reaches 100 (Position::halfmove_clock_expired, position.rs:750-752),
+ * max_plies is reached or per_game_cap positions are recorded.  counts[g] = positions recorded. */
+int pabi_cuda_random_playouts(pabi_cuda_ctx* ctx, const pabi_position_t* starts, const uint64_t* seeds, size_t n_games,
+                              uint32_t max_plies, uint32_t stride, uint32_t per_game_cap, pabi_position_t* out,
+                              uint32_t* counts, pabi_timing_t* timing);
+
 /* ---- device-resident variants (inputs/outputs already in HBM) ------------- */
 /* Positions in the 64-byte SoA record: word w of record i at
  * records[w * stride + i].  Used by bench.py to time the kernels without copies. */

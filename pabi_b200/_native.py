@@ -77,7 +77,7 @@ EXPORTS = (
     "pabi_cuda_device", "pabi_cuda_perft", "pabi_cuda_perft_batch", "pabi_cuda_perft_shard", "pabi_cuda_perft_multi", "pabi_cuda_perft_divide",
     "pabi_cuda_generate_moves_batch", "pabi_cuda_count_moves_batch", "pabi_cuda_in_check_batch",
     "pabi_cuda_attack_info_batch", "pabi_cuda_make_moves_batch", "pabi_cuda_expand_batch", "pabi_cuda_pack_records",
-    "pabi_cuda_generate_moves_device",
+    "pabi_cuda_generate_moves_device", "pabi_cuda_random_playouts",
 )
 
 _lib = None
@@ -124,6 +124,7 @@ def lib() -> C.CDLL:
     L.pabi_cuda_attack_info_batch.argtypes = [vp, vp, sz, vp, T]
     L.pabi_cuda_make_moves_batch.argtypes = [vp, vp, vp, sz, vp, T]
     L.pabi_cuda_expand_batch.argtypes = [vp, vp, sz, vp, vp, sz, T]
+    L.pabi_cuda_random_playouts.argtypes = [vp, vp, vp, sz, u32, u32, u32, vp, vp, T]
     L.pabi_cuda_pack_records.argtypes = [vp, vp, sz, vp, sz]
     L.pabi_cuda_generate_moves_device.argtypes = [vp, vp, sz, sz, vp, vp, sz, u64p, T]
     _lib = L

@@ -199,6 +199,21 @@ class Engine:
         self.last_timing = t
         return out
 
+    def random_playouts(self, starts, seeds, max_plies: int, stride: int = 1) -> List[np.ndarray]:
+        """Seeded random playouts on the device (`pabi_cuda_random_playouts`): one array of recorded
+        positions per game."""
+        arr = _as_array(starts)
+        sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
+        if len(sd) != len(arr):
+            raise ValueError("one seed per game")
+        cap = max_plies // stride + 1
+        out = np.empty(len(arr) * cap, dtype=POSITION_DTYPE)
+        counts, t = np.zeros(len(arr), dtype=np.uint32), Timing()
+        self._check(_native.lib().pabi_cuda_random_playouts(self._ctx, arr.ctypes.data, sd.ctypes.data, len(arr), max_plies, stride,
+                                                            cap, out.ctypes.data, counts.ctypes.data, C.byref(t)))
+        self.last_timing = t
+        return [out[g * cap: g * cap + int(counts[g])] for g in range(len(arr))]
+
     def expand_batch(self, positions) -> Tuple[np.ndarray, np.ndarray]:
         """Every child of every position in generate_moves order: (offsets[n+1], children)."""
         arr = _as_array(positions)

@@ -427,6 +427,7 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     CK(cudaFuncSetAttribute(k_in_check, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_attack_info, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_make_moves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_random_playouts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     if (const char* v = std::getenv("PABI_TILE_VARIANT")) {
       ctx->tile_variant = std::atoi(v);
       if (ctx->tile_variant < 0 || ctx->tile_variant >= TILE_VARIANTS) ctx->tile_variant = 0;
@@ -587,6 +588,39 @@ int pabi_cuda_attack_info_batch(pabi_cuda_ctx* ctx, const pabi_position_t* posit
     timer.end_device();
     CK(cudaMemcpyAsync(out, d_out, 5 * n * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     timer.finish(timing, 104 * n);
+    return 0;
+  } catch (const CudaFail& f) {
+    return fail(ctx, f);
+  }
+}
+
+int pabi_cuda_random_playouts(pabi_cuda_ctx* ctx, const pabi_position_t* starts, const uint64_t* seeds, size_t n_games,
+                              uint32_t max_plies, uint32_t stride, uint32_t per_game_cap, pabi_position_t* out,
+                              uint32_t* counts, pabi_timing_t* timing) {
+  if (!ctx || (n_games && (!starts || !seeds || !out || !counts))) return bad_arg(ctx, "null argument");
+  if (stride == 0 || per_game_cap == 0) return bad_arg(ctx, "stride and per_game_cap must be positive");
+  try {
+    CK(cudaSetDevice(ctx->device));
+    CallTimer timer(ctx);
+    if (n_games == 0) {
+      timer.begin_device(), timer.end_device(), timer.finish(timing, 0);
+      return 0;
+    }
+    upload_roots(ctx, starts, n_games);
+    Level& l0 = ctx->levels[0];
+    const size_t slots = n_games * (size_t)per_game_cap;
+    u64* d_seeds = (u64*)ensure(ctx, 1, n_games * sizeof(u64));
+    u32* d_counts = (u32*)ensure(ctx, 2, n_games * sizeof(u32));
+    PositionImage* d_out = (PositionImage*)ensure(ctx, 3, slots * sizeof(PositionImage));
+    CK(cudaMemcpyAsync(d_seeds, seeds, n_games * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    timer.begin_device();
+    k_random_playouts<<<grid_for(ctx, n_games, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(
+        ctx->dt, l0.rec, l0.cap, n_games, d_seeds, max_plies, stride, per_game_cap, d_out, d_counts);
+    LAUNCHED();
+    timer.end_device();
+    CK(cudaMemcpyAsync(counts, d_counts, n_games * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out, d_out, slots * sizeof(PositionImage), cudaMemcpyDeviceToHost, ctx->stream));
+    timer.finish(timing, 0);
     return 0;
   } catch (const CudaFail& f) {
     return fail(ctx, f);

@@ -235,6 +235,70 @@ __global__ void k_unpack(const u64* __restrict__ rec, size_t stride, size_t n, P
   }
 }
 
+__device__ __forceinline__ PositionImage image_of(const Pos& p) {
+  PositionImage q;
+  const u64 w = p.white;
+  q.white[0] = p.kings & w, q.black[0] = p.kings & ~w;
+  q.white[1] = p.queens & w, q.black[1] = p.queens & ~w;
+  q.white[2] = p.rooks & w, q.black[2] = p.rooks & ~w;
+  q.white[3] = p.bishops & w, q.black[3] = p.bishops & ~w;
+  q.white[4] = p.knights & w, q.black[4] = p.knights & ~w;
+  q.white[5] = p.pawns & w, q.black[5] = p.pawns & ~w;
+  q.hash = 0;
+  q.fullmove = (u16)meta_fullmove(p.meta);
+  q.castling = (u8)meta_castling(p.meta);
+  q.stm = (u8)meta_stm(p.meta);
+  q.halfmove = (u8)meta_halfmove(p.meta);
+  q.ep = (u8)meta_ep(p.meta);
+  q.pad[0] = q.pad[1] = 0;
+  return q;
+}
+
+__device__ __forceinline__ u64 splitmix64(u64& s) {
+  u64 z = (s += 0x9E3779B97F4A7C15ULL);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+
+/* Seeded uniform-random playouts, one thread per game: the position source of the datagen-style
+ * workload (BASELINE.json configs[4]; the loop a src/datagen driver would run around
+ * generate_moves / make_move, position.rs:317-433).  At each ply the move is
+ * moves[splitmix64(seed) % n] in generate_moves order; the position after every stride-th ply is
+ * recorded until there is no legal move, the halfmove clock reaches 100
+ * (Position::halfmove_clock_expired, position.rs:750-752), max_plies, or the game's slots are used. */
+__global__ void __launch_bounds__(FLAT_THREADS)
+k_random_playouts(DeviceTables dt, const u64* __restrict__ rec, size_t stride_rec, size_t n_games, const u64* __restrict__ seeds,
+                  u32 max_plies, u32 stride, u32 per_game_cap, PositionImage* __restrict__ out, u32* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SharedTables* st = reinterpret_cast<SharedTables*>(smem);
+  stage_tables(st, dt.image);
+  const Tables tb{st, dt.g};
+  for (size_t g = (size_t)blockIdx.x * FLAT_THREADS + threadIdx.x; g < n_games; g += (size_t)gridDim.x * FLAT_THREADS) {
+    Pos p = load_pos(rec, stride_rec, g);
+    u64 seed = seeds[g];
+    u32 written = 0;
+    PositionImage* slot = out + g * per_game_cap;
+    for (u32 ply = 0;; ply++) {
+      if (ply % stride == 0) {
+        if (written >= per_game_cap) break;
+        slot[written++] = image_of(p);
+      }
+      if (ply >= max_plies || meta_halfmove(p.meta) >= 100) break;
+      const u32 n = count_moves(p, tb);
+      if (n == 0) break;
+      const u32 pick = (u32)(splitmix64(seed) % n);
+      u32 k = 0;
+      u16 chosen = 0;
+      generate_moves(p, tb, [&](int from, int to, int promo, int) {
+        if (k++ == pick) chosen = pack_move(from, to, promo);
+      });
+      make_move(p, tb, chosen);
+    }
+    counts[g] = written;
+  }
+}
+
 /* every shard_count-th record starting at shard_index (root-subtree sharding) */
 __global__ void k_gather_shard(Frontier in, size_t n_out, u32 shard_index, u32 shard_count, Frontier out) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (size_t)gridDim.x * blockDim.x) {

@@ -75,6 +75,8 @@ extern "C" {
                                       out: *mut RawPosition, t: *mut Timing) -> i32;
     pub fn pabi_cuda_expand_batch(ctx: *mut Ctx, positions: *const RawPosition, n: usize, offsets: *mut u32,
                                   children: *mut RawPosition, children_cap: usize, t: *mut Timing) -> i32;
+    pub fn pabi_cuda_random_playouts(ctx: *mut Ctx, starts: *const RawPosition, seeds: *const u64, n_games: usize, max_plies: u32,
+                                     stride: u32, per_game_cap: u32, out: *mut RawPosition, counts: *mut u32, t: *mut Timing) -> i32;
     pub fn pabi_cuda_pack_records(ctx: *mut Ctx, positions: *const RawPosition, n: usize, device_records: *mut u64,
                                   stride: usize) -> i32;
     pub fn pabi_cuda_generate_moves_device(ctx: *mut Ctx, device_records: *const u64, stride: usize, n: usize,

@@ -216,6 +216,27 @@ def test_children_equal_oracle_children(engine, playout_positions):
     assert k == len(children)
 
 
+def test_random_playouts_on_device_equal_the_oracle_driver(pb, engine):
+    """The datagen-style position source run on the device: every recorded position of every game equals
+    the CPU driver's (oracle_random_playout), clocks and en passant squares included."""
+    import workloads
+    fens = workloads.chess324_fens()
+    starts, seeds = [], []
+    for g in range(600):
+        starts.append(oracle.starting() if g % 2 == 0 else oracle.parse(fens[(g // 2) % 324]))
+        seeds.append(0x5EED0000 + g)
+    start_arr = oracle.positions_array(starts)
+    for max_plies, stride in ((200, 1), (40, 3), (0, 1)):
+        games = engine.random_playouts(start_arr, seeds, max_plies, stride)
+        total = 0
+        for g, got in enumerate(games):
+            want = oracle.random_playout(starts[g], seeds[g], max_plies, stride)
+            want["hash"] = 0
+            assert got.tobytes() == want.tobytes(), (g, max_plies, stride)
+            total += len(got)
+        assert total >= 600
+
+
 # ---- text API through the same library (tests/chess.rs:33-181) ----
 
 def test_fen_round_trips_and_errors(pb, vectors):
