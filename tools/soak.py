@@ -1,0 +1,60 @@
+"""One-off differential soak on cuda:0 (not part of pytest): large random samples, CUDA path vs oracle.
+
+  - 3M playout positions (startpos + all Chess324 arrays): ordered move lists, counts, in_check
+  - 200k of them: perft(3) per root
+  - 20k of them: every child of the position, field for field
+"""
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+import oracle  # noqa: E402
+import workloads  # noqa: E402
+
+import pabi_b200 as pb  # noqa: E402
+
+e = pb.Engine(0)
+t0 = time.time()
+positions = workloads.playout_positions(3_000_000)
+print(f"{len(positions)} positions generated in {time.time() - t0:.1f}s", flush=True)
+off, mv = e.generate_moves_batch(positions)
+woff, wmv = oracle.generate_moves_batch(positions)
+assert np.array_equal(off, woff) and np.array_equal(mv, wmv)
+assert np.array_equal(e.count_moves_batch(positions), np.diff(woff))
+print(f"move lists: {len(mv)} moves bit-exact", flush=True)
+
+threads = os.cpu_count() or 1
+sample = np.ascontiguousarray(positions[::15][:200_000])
+got = e.perft_batch(sample, 3)
+lib = oracle.lib()
+import ctypes as C
+want = np.zeros(len(sample), dtype=np.uint64)
+for i in range(len(sample)):
+    want[i] = lib.oracle_perft(C.cast(sample.ctypes.data + 112 * i, C.POINTER(oracle.Position)), 3)
+assert np.array_equal(got, want), np.nonzero(got != want)[0][:5]
+print(f"perft(3) x {len(sample)} roots bit-exact ({int(want.sum())} nodes)", flush=True)
+
+sample = np.ascontiguousarray(positions[7::150][:20_000])
+off, children = e.expand_batch(sample)
+woff, wmv = oracle.generate_moves_batch(sample)
+assert np.array_equal(off, woff)
+buf = np.zeros(len(children), dtype=oracle.POSITION_DTYPE)
+k = 0
+for i in range(len(sample)):
+    for m in wmv[woff[i]:woff[i + 1]]:
+        C.memmove(buf.ctypes.data + 112 * k, sample.ctypes.data + 112 * i, 112)
+        lib.oracle_make_move(C.cast(buf.ctypes.data + 112 * k, C.POINTER(oracle.Position)), int(m))
+        k += 1
+buf["hash"] = 0
+assert buf.tobytes() == children.tobytes()
+print(f"children: {len(children)} positions equal field for field", flush=True)
+ic = e.in_check_batch(positions[:500_000])
+ai = e.attack_info_batch(positions[:500_000])
+assert np.array_equal(ic, ai[:, 1] != 0)
+print("soak ok", flush=True)
