@@ -1,7 +1,7 @@
 /*
  * kernels.cuh -- sm_100a kernels of the perft / move-generation path.
  *
- * K0  stage_tables        (device fn) 50 KB table image -> shared memory, once per block
+ * K0  stage_tables        (device fn) 48 KB table image -> shared memory by one TMA bulk copy per block
  * K1  k_tile<TILE_EXPAND> one breadth-first ply: parents (SoA, HBM) -> children (SoA, HBM)
  * K2  k_tile<TILE_LEAF>   last two plies fused: parents -> children in shared memory ->
  *                         count-only move generation per child, nothing written to HBM
@@ -20,13 +20,36 @@
 
 namespace pabi {
 
-/* ---- shared-memory table staging (K0) ----------------------------------- */
+/* ---- shared-memory table staging (K0) -----------------------------------
+ * One elected thread arms an mbarrier with the image size and issues a single TMA bulk copy
+ * (cp.async.bulk global -> shared, UBLKCP in SASS); every thread then waits on the barrier's phase.
+ * The copy engine moves the 48 KB while the other threads are already free to set up. */
 __device__ __forceinline__ void stage_tables(SharedTables* dst, const SharedTables* __restrict__ src) {
-  static_assert(sizeof(SharedTables) % 16 == 0, "table image must be uint4-copyable");
-  const uint4* s = reinterpret_cast<const uint4*>(src);
-  uint4* d = reinterpret_cast<uint4*>(dst);
-  for (u32 i = threadIdx.x; i < sizeof(SharedTables) / 16; i += blockDim.x) d[i] = __ldg(s + i);
+  static_assert(sizeof(SharedTables) % 16 == 0 && sizeof(SharedTables) < (1u << 20), "bulk copies are 16-byte granular; tx count < 2^20");
+  __shared__ __align__(8) unsigned long long table_barrier;
+  const u32 bar = (u32)__cvta_generic_to_shared(&table_barrier);
+  const u32 dst_s = (u32)__cvta_generic_to_shared(dst);
+  constexpr u32 BYTES = (u32)sizeof(SharedTables);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); /* make the init visible to the async proxy */
+  }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s), "l"(src),
+                 "r"(BYTES), "r"(bar)
+                 : "memory");
+  }
+  u32 done = 0;
+  for (u32 spins = 0; !done; ++spins) { /* phase 0 completes when the bytes have landed */
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar)
+        : "memory");
+    if (spins > (1u << 20)) __trap(); /* never spin forever on a copy that cannot complete */
+  }
 }
 
 struct DeviceTables {
