@@ -55,6 +55,28 @@ PB_HD int lsb(u64 x) {
 }
 PB_HD u64 bit(int sq) { return 1ULL << sq; }
 
+/* Iterates the squares of a bitboard in ascending order (BitboardIterator, bitboard.rs:303-329),
+ * one 32-bit word at a time: per step a 32-bit find-first-set and clear instead of their 64-bit
+ * forms, which matters on a 32-bit datapath whose ALU pipe is the bottleneck. */
+struct Squares {
+  u32 word, high;
+  int base;
+  PB_HD explicit Squares(u64 b) : word((u32)b), high((u32)(b >> 32)), base(0) {
+    if (!word) word = high, high = 0, base = 32;
+  }
+  PB_HD bool any() const { return word != 0; }
+  PB_HD int pop() {
+#ifdef __CUDA_ARCH__
+    const int sq = base + __ffs((int)word) - 1;
+#else
+    const int sq = base + __builtin_ctz(word);
+#endif
+    word &= word - 1;
+    if (!word) word = high, high = 0, base = 32;
+    return sq;
+  }
+};
+
 /* ---- constants --------------------------------------------------------- */
 constexpr u64 FILE_A = 0x0101010101010101ULL;
 constexpr u64 FILE_H = 0x8080808080808080ULL;
@@ -469,13 +491,13 @@ PB_HD u32 count_moves_white(u64 our, u64 pawns, u64 knights, u64 bishops, u64 ro
      * tested against fewer squares and the scan stops when nothing is left */
     const u64 occ_nk = occ ^ king_bb;
     u64 rem = need & ~(tb.king(lsb(kings & their)) | pawn_attacks(pawns & their, 1));
-    for (u64 b = knights & their & tb.s->knight_zone[king]; b; b &= b - 1) rem &= ~tb.knight(lsb(b));
-    for (u64 b = their_diag & tb.s->diag_zone[king]; b && rem; b &= b - 1) {
-      const int sq = lsb(b);
+    for (Squares b(knights & their & tb.s->knight_zone[king]); b.any();) rem &= ~tb.knight(b.pop());
+    for (Squares b(their_diag & tb.s->diag_zone[king]); b.any() && rem;) {
+      const int sq = b.pop();
       if ((tb.s->diag[sq] | tb.s->anti[sq]) & rem) rem &= ~tb.bishop(sq, occ_nk);
     }
-    for (u64 b = their_orth & tb.s->orth_zone[king]; b && rem; b &= b - 1) {
-      const int sq = lsb(b);
+    for (Squares b(their_orth & tb.s->orth_zone[king]); b.any() && rem;) {
+      const int sq = b.pop();
       if (tb.s->orth[sq] & rem) rem &= ~tb.rook(sq, occ_nk);
     }
     n = popc(king_targets & rem);
@@ -510,19 +532,19 @@ PB_HD u32 count_moves_white(u64 our, u64 pawns, u64 knights, u64 bishops, u64 ro
 
   const u64 not_our = ~our;
   const u64 targets = not_our & block;
-  for (u64 b = knights & our & ~pins; b; b &= b - 1) n += popc(tb.knight(lsb(b)) & targets);
+  for (Squares b(knights & our & ~pins); b.any();) n += popc(tb.knight(b.pop()) & targets);
   /* sliders hemmed in by our own pieces (no neighbour on their lines that is not ours) have no
    * moves and need no lookup; found set-wise */
   const u64 orth_open = (not_our >> 8) | (not_our << 8) | ((not_our >> 1) & ~FILE_H) | ((not_our << 1) & ~FILE_A);
   const u64 diag_open = (((not_our >> 9) | (not_our << 7)) & ~FILE_H) | (((not_our >> 7) | (not_our << 9)) & ~FILE_A);
-  for (u64 b = (rooks | queens) & our & orth_open; b; b &= b - 1) {
-    const int from = lsb(b);
+  for (Squares b((rooks | queens) & our & orth_open); b.any();) {
+    const int from = b.pop();
     u64 t = tb.rook(from, occ) & targets;
     if ((pins >> from) & 1) t &= tb.line(king, from);
     n += popc(t);
   }
-  for (u64 b = (bishops | queens) & our & diag_open; b; b &= b - 1) {
-    const int from = lsb(b);
+  for (Squares b((bishops | queens) & our & diag_open); b.any();) {
+    const int from = b.pop();
     u64 t = tb.bishop(from, occ) & targets;
     if ((pins >> from) & 1) t &= tb.line(king, from);
     n += popc(t);
@@ -599,30 +621,30 @@ PB_HD u32 generate_moves(const Pos& p, const TB& tb, Emit&& emit) {
   analyze<US>(p, tb, a);
   u32 n = 0;
   /* generate_king_moves, position.rs:1034-1040 */
-  for (u64 t = a.safe_king; t; t &= t - 1, ++n) emit(a.king, lsb(t), 0, KIND_KING);
+  for (Squares t(a.safe_king); t.any(); ++n) emit(a.king, t.pop(), 0, KIND_KING);
   if (a.block == 0) return n;
   const u64 targets = ~a.our & a.block;
 
   /* generate_knight_moves, position.rs:1042-1059 */
-  for (u64 b = p.knights & a.our & ~a.pins; b; b &= b - 1) {
-    const int from = lsb(b);
-    for (u64 t = tb.knight(from) & targets; t; t &= t - 1, ++n) emit(from, lsb(t), 0, KIND_KNIGHT);
+  for (Squares b(p.knights & a.our & ~a.pins); b.any();) {
+    const int from = b.pop();
+    for (Squares t(tb.knight(from) & targets); t.any(); ++n) emit(from, t.pop(), 0, KIND_KNIGHT);
   }
   /* generate_rook_moves over rooks|queens, position.rs:1061-1081 */
-  for (u64 b = (p.rooks | p.queens) & a.our; b; b &= b - 1) {
-    const int from = lsb(b);
+  for (Squares b((p.rooks | p.queens) & a.our); b.any();) {
+    const int from = b.pop();
     u64 t = tb.rook(from, a.occ) & targets;
     if ((a.pins >> from) & 1) t &= tb.line(a.king, from);
     const int kind = (p.queens >> from) & 1 ? KIND_QUEEN : KIND_ROOK;
-    for (; t; t &= t - 1, ++n) emit(from, lsb(t), 0, kind);
+    for (Squares ts(t); ts.any(); ++n) emit(from, ts.pop(), 0, kind);
   }
   /* generate_bishop_moves over bishops|queens, position.rs:1083-1104 */
-  for (u64 b = (p.bishops | p.queens) & a.our; b; b &= b - 1) {
-    const int from = lsb(b);
+  for (Squares b((p.bishops | p.queens) & a.our); b.any();) {
+    const int from = b.pop();
     u64 t = tb.bishop(from, a.occ) & targets;
     if ((a.pins >> from) & 1) t &= tb.line(a.king, from);
     const int kind = (p.queens >> from) & 1 ? KIND_QUEEN : KIND_BISHOP;
-    for (; t; t &= t - 1, ++n) emit(from, lsb(t), 0, kind);
+    for (Squares ts(t); ts.any(); ++n) emit(from, ts.pop(), 0, kind);
   }
 
   /* generate_pawn_moves, position.rs:1106-1224 */
@@ -630,13 +652,12 @@ PB_HD u32 generate_moves(const Pos& p, const TB& tb, Emit&& emit) {
   const int last_rank = a.us == 0 ? 7 : 0;
   const u64 capture_targets = a.their & a.block;
   /* captures: per pawn ascending, per target ascending (:1123-1142) */
-  for (u64 b = ps.west | ps.east; b; b &= b - 1) {
-    const u64 from_bb = b & (0 - b);
-    const int from = lsb(b);
-    u64 t = (pawn_attacks_west(from_bb & ps.west, a.us) | pawn_attacks_east(from_bb & ps.east, a.us)) &
-            capture_targets;
-    for (; t; t &= t - 1) {
-      const int to = lsb(t);
+  for (Squares b(ps.west | ps.east); b.any();) {
+    const int from = b.pop();
+    const u64 from_bb = bit(from);
+    const u64 t = (pawn_attacks_west(from_bb & ps.west, a.us) | pawn_attacks_east(from_bb & ps.east, a.us)) & capture_targets;
+    for (Squares ts(t); ts.any();) {
+      const int to = ts.pop();
       if ((to >> 3) == last_rank) {
         emit(from, to, PROMO_Q, KIND_PAWN), emit(from, to, PROMO_R, KIND_PAWN), emit(from, to, PROMO_B, KIND_PAWN),
             emit(from, to, PROMO_N, KIND_PAWN);
@@ -653,8 +674,8 @@ PB_HD u32 generate_moves(const Pos& p, const TB& tb, Emit&& emit) {
   const u64 empty = ~a.occ;
   const u64 single_all = push(ps.pushers, a.us) & empty;
   const int back = a.us == 0 ? -8 : 8;
-  for (u64 t = single_all & a.block; t; t &= t - 1) {
-    const int to = lsb(t);
+  for (Squares t(single_all & a.block); t.any();) {
+    const int to = t.pop();
     if ((to >> 3) == last_rank) {
       emit(to + back, to, PROMO_Q, KIND_PAWN), emit(to + back, to, PROMO_R, KIND_PAWN),
           emit(to + back, to, PROMO_B, KIND_PAWN), emit(to + back, to, PROMO_N, KIND_PAWN);
@@ -664,8 +685,10 @@ PB_HD u32 generate_moves(const Pos& p, const TB& tb, Emit&& emit) {
     }
   }
   /* double pushes in ascending target order (:1205-1223) */
-  for (u64 t = push(single_all & (a.us == 0 ? RANK_3 : RANK_6), a.us) & empty & a.block; t; t &= t - 1, ++n)
-    emit(lsb(t) + 2 * back, lsb(t), 0, KIND_PAWN);
+  for (Squares t(push(single_all & (a.us == 0 ? RANK_3 : RANK_6), a.us) & empty & a.block); t.any(); ++n) {
+    const int to = t.pop();
+    emit(to + 2 * back, to, 0, KIND_PAWN);
+  }
   /* generate_castle_moves: short, then long (:1236-1286) */
   const int c = castle_moves(p, a);
   const int home = 4 + 56 * a.us;
