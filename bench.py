@@ -209,10 +209,14 @@ def run_gpu(args) -> None:
         achieved = leaf_bytes / (leaf_ms * 1e-3) / 1e9 if leaf_ms else 0.0
         # DRAM traffic of the leaf kernel from the committed ncu --set full capture (profiles/): the kernel only
         # reads its parents, so the capture's bytes per parent scale to this run's launch size
-        traffic = traffic_note = None
+        traffic = traffic_note = issue = None
         prof = ROOT / "profiles" / "leaf_kernel_traffic.json"
         if prof.exists() and leaf_launches:
             t = json.loads(prof.read_text())
+            # what actually limits the kernel (ncu capture, not measured in this run): the integer ALU pipe
+            issue = {k: t[k] for k in ("alu_pipe_pct_of_peak", "issue_active_pct", "xu_pipe_pct", "lsu_pipe_pct", "fma_pipe_pct",
+                                       "thread_inst_per_warp_inst", "l1_hit_rate_pct", "dram_throughput_pct") if k in t}
+            issue["source"] = t["source"]
             traffic = t["dram_bytes_per_parent"] * leaf_parents / leaf_launches
             traffic_note = (f"{t['dram_bytes_per_parent']:.1f} B/parent (dram__bytes_read+write of the ncu capture, "
                             f"{t['parents_in_capture']} parents) x {leaf_parents // leaf_launches} parents per launch")
@@ -232,6 +236,7 @@ def run_gpu(args) -> None:
             "roofline": {"bound": "hbm", "kernel": "k_tile<LEAF=true> (fused last two plies)", "achieved": achieved,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          "peak_source": peaks["source"], "traffic": traffic, "traffic_note": traffic_note,
+                         "limiter_from_ncu": issue,
                          "algorithmic_bytes_per_launch": leaf_bytes / max(1, leaf_launches),
                          "avg_launch_ms": leaf_ms / max(1, leaf_launches), "launches": leaf_launches,
                          "share_of_step": leaf_ms / device_ms if device_ms else None,
