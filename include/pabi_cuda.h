@@ -149,6 +149,32 @@ int pabi_cuda_random_playouts(pabi_cuda_ctx* ctx, const pabi_position_t* starts,
                               uint32_t max_plies, uint32_t stride, uint32_t per_game_cap, pabi_position_t* out,
                               uint32_t* counts, pabi_timing_t* timing);
 
+/* ---- Game environment: `Game` (src/chess/game.rs:21-111) for a batch of games ------------------
+ * State lives on the device: position, perspective (the root's side to move, game.rs:36), the
+ * repetition table (src/chess/zobrist.rs:10-36) and the threefold flag.  The Syzygy adjudication
+ * branch of Game::result (game.rs:72-96) needs the third-party shakmaty-syzygy prober and tablebase
+ * files and is not provided: results are those of the reference with no tablebase loaded.
+ * Result codes: 0 = None, 1 = Win, 2 = Draw, 3 = Loss (GameResult, src/environment.rs:56-61, from
+ * the perspective of the player to move at the root). */
+typedef struct pabi_cuda_games pabi_cuda_games;
+#define PABI_NO_MOVE 0xFFFFu
+/* Game::new for n roots (game.rs:30-47); history_cap = most actions a game will ever receive */
+int pabi_cuda_games_create(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, uint32_t history_cap,
+                           pabi_cuda_games** out);
+void pabi_cuda_games_destroy(pabi_cuda_games* games);
+/* Game::actions (game.rs:50-52) of every game, CSR like pabi_cuda_generate_moves_batch */
+int pabi_cuda_games_actions(pabi_cuda_games* games, uint32_t* offsets /* [n+1] */, pabi_move_t* moves, size_t moves_cap);
+/* Game::apply (game.rs:54-59): actions[g] is applied to game g; PABI_NO_MOVE leaves it untouched */
+int pabi_cuda_games_apply(pabi_cuda_games* games, const pabi_move_t* actions /* [n] */);
+/* Game::result (game.rs:61-110) */
+int pabi_cuda_games_result(pabi_cuda_games* games, uint8_t* results /* [n] */);
+/* the current Position of every game */
+int pabi_cuda_games_positions(pabi_cuda_games* games, pabi_position_t* out /* [n] */);
+/* Uniformly random self-play entirely on the device: in every game, actions()[splitmix64(seed) % len] is
+ * applied until result() is Some or max_plies actions were applied.  plies[g] = actions applied by this call. */
+int pabi_cuda_games_play_random(pabi_cuda_games* games, const uint64_t* seeds /* [n] */, uint32_t max_plies,
+                                uint8_t* results /* [n] */, uint32_t* plies /* [n] */, pabi_timing_t* timing);
+
 /* ---- device-resident variants (inputs/outputs already in HBM) ------------- */
 /* Positions in the 64-byte SoA record: word w of record i at
  * records[w * stride + i].  Used by bench.py to time the kernels without copies. */

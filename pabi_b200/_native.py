@@ -78,6 +78,8 @@ EXPORTS = (
     "pabi_cuda_generate_moves_batch", "pabi_cuda_count_moves_batch", "pabi_cuda_in_check_batch",
     "pabi_cuda_attack_info_batch", "pabi_cuda_make_moves_batch", "pabi_cuda_expand_batch", "pabi_cuda_pack_records",
     "pabi_cuda_generate_moves_device", "pabi_cuda_random_playouts",
+    "pabi_cuda_games_create", "pabi_cuda_games_destroy", "pabi_cuda_games_actions", "pabi_cuda_games_apply",
+    "pabi_cuda_games_result", "pabi_cuda_games_positions", "pabi_cuda_games_play_random",
 )
 
 _lib = None
@@ -125,6 +127,14 @@ def lib() -> C.CDLL:
     L.pabi_cuda_make_moves_batch.argtypes = [vp, vp, vp, sz, vp, T]
     L.pabi_cuda_expand_batch.argtypes = [vp, vp, sz, vp, vp, sz, T]
     L.pabi_cuda_random_playouts.argtypes = [vp, vp, vp, sz, u32, u32, u32, vp, vp, T]
+    L.pabi_cuda_games_create.argtypes = [vp, vp, sz, u32, C.POINTER(vp)]
+    L.pabi_cuda_games_destroy.argtypes = [vp]
+    L.pabi_cuda_games_destroy.restype = None
+    L.pabi_cuda_games_actions.argtypes = [vp, vp, vp, sz]
+    L.pabi_cuda_games_apply.argtypes = [vp, vp]
+    L.pabi_cuda_games_result.argtypes = [vp, vp]
+    L.pabi_cuda_games_positions.argtypes = [vp, vp]
+    L.pabi_cuda_games_play_random.argtypes = [vp, vp, u32, vp, vp, T]
     L.pabi_cuda_pack_records.argtypes = [vp, vp, sz, vp, sz]
     L.pabi_cuda_generate_moves_device.argtypes = [vp, vp, sz, sz, vp, vp, sz, u64p, T]
     _lib = L

@@ -830,4 +830,23 @@ PB_HD void make_move_kind(Pos& p, const TB& tb, u16 mv, int kind) {
   p.meta = make_meta(castling, ep, us ^ 1, 0, 0);
 }
 
+/* 64-bit key with the equality semantics of the reference's `Position::hash()` AS MAINTAINED BY
+ * make_move, which is what the repetition table sees (game.rs:56, zobrist.rs:10-36).  make_move
+ * toggles the piece and castling keys (position.rs:442-466, :491-497, ...) but never toggles
+ * BLACK_TO_MOVE (only compute_hash does, :780) and never removes an en passant key once set
+ * (:614 is the only use), so within a game two positions have equal hashes exactly when placement
+ * and castling rights are equal -- side to move and en passant square do not take part.  The key
+ * below is over exactly those fields.  (The Zobrist values themselves are build-random,
+ * generated.rs:15-16; different positions collide with probability ~2^-64 here as there.) */
+PB_HD u64 position_key(const Pos& p) {
+  u64 h = 0x9E3779B97F4A7C15ULL;
+  const u64 words[8] = {p.white, p.pawns, p.knights, p.bishops, p.rooks, p.queens, p.kings, p.meta & 0xFULL};
+  for (int i = 0; i < 8; i++) {
+    h = (h ^ words[i]) * 0xBF58476D1CE4E5B9ULL;
+    h ^= h >> 29;
+  }
+  h *= 0x94D049BB133111EBULL;
+  return h ^ (h >> 32);
+}
+
 } /* namespace pabi */

@@ -428,6 +428,9 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     CK(cudaFuncSetAttribute(k_attack_info, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_make_moves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_random_playouts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_games_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_games_result, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_games_play_random, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     if (const char* v = std::getenv("PABI_TILE_VARIANT")) {
       ctx->tile_variant = std::atoi(v);
       if (ctx->tile_variant < 0 || ctx->tile_variant >= TILE_VARIANTS) ctx->tile_variant = 0;
@@ -622,6 +625,171 @@ int pabi_cuda_random_playouts(pabi_cuda_ctx* ctx, const pabi_position_t* starts,
     CK(cudaMemcpyAsync(out, d_out, slots * sizeof(PositionImage), cudaMemcpyDeviceToHost, ctx->stream));
     timer.finish(timing, 0);
     return 0;
+  } catch (const CudaFail& f) {
+    return fail(ctx, f);
+  }
+}
+
+} /* extern "C" */
+
+struct pabi_cuda_games {
+  pabi_cuda_ctx* ctx = nullptr;
+  GamesState gs{};
+  u16* d_actions = nullptr;
+  u8* d_results = nullptr;
+  u32* d_applied = nullptr;
+  u64* d_seeds = nullptr;
+};
+
+namespace {
+int games_overflowed(pabi_cuda_games* games) {
+  pabi_cuda_ctx* ctx = games->ctx;
+  u32 overflow = 0;
+  CK(cudaMemcpyAsync(&overflow, games->gs.overflow, sizeof overflow, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (overflow) {
+    CK(cudaMemsetAsync(games->gs.overflow, 0, sizeof(u32), ctx->stream));
+    ctx->error = "a game received more actions than history_cap";
+    return -4;
+  }
+  return 0;
+}
+} /* namespace */
+
+extern "C" {
+
+int pabi_cuda_games_create(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, uint32_t history_cap,
+                           pabi_cuda_games** out) {
+  if (!ctx || !out || !roots || n == 0) return bad_arg(ctx, "null argument or no games");
+  *out = nullptr;
+  pabi_cuda_games* games = new (std::nothrow) pabi_cuda_games;
+  if (!games) return -3;
+  games->ctx = ctx;
+  try {
+    CK(cudaSetDevice(ctx->device));
+    GamesState& gs = games->gs;
+    gs.n = n, gs.history_cap = history_cap;
+    CK(cudaMalloc(&gs.rec, n * POS_WORDS * sizeof(u64)));
+    CK(cudaMalloc(&gs.keys, n * ((size_t)history_cap + 1) * sizeof(u64)));
+    CK(cudaMalloc(&gs.plies, n * sizeof(u32)));
+    CK(cudaMalloc(&gs.perspective, n));
+    CK(cudaMalloc(&gs.threefold, n));
+    CK(cudaMalloc(&gs.overflow, sizeof(u32)));
+    CK(cudaMalloc(&games->d_actions, n * sizeof(u16)));
+    CK(cudaMalloc(&games->d_results, n));
+    CK(cudaMalloc(&games->d_applied, n * sizeof(u32)));
+    CK(cudaMalloc(&games->d_seeds, n * sizeof(u64)));
+    CK(cudaMemsetAsync(gs.overflow, 0, sizeof(u32), ctx->stream));
+    void* staging = ensure(ctx, 0, n * sizeof(pabi_position_t));
+    CK(cudaMemcpyAsync(staging, roots, n * sizeof(pabi_position_t), cudaMemcpyHostToDevice, ctx->stream));
+    k_pack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>((const PositionImage*)staging, n, gs.rec, n, 0, nullptr);
+    CK(cudaGetLastError());
+    k_games_init<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(gs);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+  } catch (const CudaFail& f) {
+    pabi_cuda_games_destroy(games);
+    return fail(ctx, f);
+  }
+  *out = games;
+  return 0;
+}
+
+void pabi_cuda_games_destroy(pabi_cuda_games* games) {
+  if (!games) return;
+  cudaSetDevice(games->ctx->device);
+  cudaStreamSynchronize(games->ctx->stream);
+  GamesState& gs = games->gs;
+  cudaFree(gs.rec), cudaFree(gs.keys), cudaFree(gs.plies), cudaFree(gs.perspective), cudaFree(gs.threefold), cudaFree(gs.overflow);
+  cudaFree(games->d_actions), cudaFree(games->d_results), cudaFree(games->d_applied), cudaFree(games->d_seeds);
+  delete games;
+}
+
+int pabi_cuda_games_actions(pabi_cuda_games* games, uint32_t* offsets, pabi_move_t* moves, size_t moves_cap) {
+  if (!games || !offsets || (moves_cap && !moves)) return -1;
+  pabi_cuda_ctx* ctx = games->ctx;
+  try {
+    const size_t n = games->gs.n;
+    u32* d_offsets = (u32*)ensure(ctx, 1, (n + 1) * sizeof(u32));
+    u16* d_moves = moves_cap ? (u16*)ensure(ctx, 2, moves_cap * sizeof(u16)) : nullptr;
+    uint64_t total = 0;
+    const int rc = pabi_cuda_generate_moves_device(ctx, games->gs.rec, n, n, d_offsets, d_moves, moves_cap, &total, nullptr);
+    if (rc != 0 && rc != -2) return rc;
+    CK(cudaMemcpyAsync(offsets, d_offsets, (n + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    if (total <= moves_cap && total) CK(cudaMemcpyAsync(moves, d_moves, total * sizeof(u16), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return total > moves_cap ? -2 : 0;
+  } catch (const CudaFail& f) {
+    return fail(ctx, f);
+  }
+}
+
+int pabi_cuda_games_apply(pabi_cuda_games* games, const pabi_move_t* actions) {
+  if (!games || !actions) return -1;
+  pabi_cuda_ctx* ctx = games->ctx;
+  try {
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = games->gs.n;
+    CK(cudaMemcpyAsync(games->d_actions, actions, n * sizeof(u16), cudaMemcpyHostToDevice, ctx->stream));
+    k_games_apply<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, games->gs, games->d_actions);
+    CK(cudaGetLastError());
+    return games_overflowed(games);
+  } catch (const CudaFail& f) {
+    return fail(ctx, f);
+  }
+}
+
+int pabi_cuda_games_result(pabi_cuda_games* games, uint8_t* results) {
+  if (!games || !results) return -1;
+  pabi_cuda_ctx* ctx = games->ctx;
+  try {
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = games->gs.n;
+    k_games_result<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, games->gs, games->d_results);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(results, games->d_results, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  } catch (const CudaFail& f) {
+    return fail(ctx, f);
+  }
+}
+
+int pabi_cuda_games_positions(pabi_cuda_games* games, pabi_position_t* out) {
+  if (!games || !out) return -1;
+  pabi_cuda_ctx* ctx = games->ctx;
+  try {
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = games->gs.n;
+    PositionImage* d_out = (PositionImage*)ensure(ctx, 3, n * sizeof(PositionImage));
+    k_unpack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(games->gs.rec, n, n, d_out);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_out, n * sizeof(PositionImage), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  } catch (const CudaFail& f) {
+    return fail(ctx, f);
+  }
+}
+
+int pabi_cuda_games_play_random(pabi_cuda_games* games, const uint64_t* seeds, uint32_t max_plies, uint8_t* results,
+                                uint32_t* plies, pabi_timing_t* timing) {
+  if (!games || !seeds || !results || !plies) return -1;
+  pabi_cuda_ctx* ctx = games->ctx;
+  try {
+    CK(cudaSetDevice(ctx->device));
+    CallTimer timer(ctx);
+    const size_t n = games->gs.n;
+    CK(cudaMemcpyAsync(games->d_seeds, seeds, n * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    timer.begin_device();
+    k_games_play_random<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(
+        ctx->dt, games->gs, games->d_seeds, max_plies, games->d_results, games->d_applied);
+    LAUNCHED();
+    timer.end_device();
+    CK(cudaMemcpyAsync(results, games->d_results, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(plies, games->d_applied, n * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    timer.finish(timing, 0);
+    return games_overflowed(games);
   } catch (const CudaFail& f) {
     return fail(ctx, f);
   }

@@ -322,6 +322,125 @@ k_random_playouts(DeviceTables dt, const u64* __restrict__ rec, size_t stride_re
   }
 }
 
+/* ---- Game environment (game.rs:21-111 without the Syzygy branch), one thread per game ------- */
+struct GamesState {
+  u64* rec;          /* SoA records, stride n */
+  u64* keys;         /* keys[g * (history_cap + 1) + k]: key after k actions (RepetitionTable, zobrist.rs:10-36) */
+  u32* plies;        /* actions applied so far */
+  u8* perspective;   /* side to move at the root (game.rs:36) */
+  u8* threefold;     /* RepetitionTable::record() of the last apply (game.rs:56) */
+  u32* overflow;     /* number of applies refused because the history was full */
+  size_t n;
+  u32 history_cap;
+};
+
+/* RepetitionTable::record (zobrist.rs:28-32): true exactly when the key has now been seen 3 times */
+__device__ __forceinline__ bool record_key(const GamesState& gs, size_t g, u32 ply_after, u64 key) {
+  u64* keys = gs.keys + g * ((size_t)gs.history_cap + 1);
+  int count = 1;
+  for (u32 k = 0; k < ply_after; k++) count += keys[k] == key;
+  keys[ply_after] = key;
+  return count == 3;
+}
+
+/* Game::result (game.rs:61-110): 0 none, 1 win, 2 draw, 3 loss, from the root player's perspective */
+template <class TB>
+__device__ __forceinline__ int game_result(const Pos& p, const TB& tb, bool threefold, int perspective, u32 n_moves) {
+  if (threefold) return 2;
+  if (meta_halfmove(p.meta) >= 100) return 2; /* Position::halfmove_clock_expired, position.rs:750-752 */
+  if (n_moves == 0) {
+    Analysis a;
+    analyze(p, tb, a);
+    if (a.checkers == 0) return 2;                       /* stalemate */
+    return perspective == meta_stm(p.meta) ? 3 : 1;      /* the player to move is mated */
+  }
+  return 0;
+}
+
+__global__ void k_games_init(GamesState gs) { /* Game::new, game.rs:30-47 */
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < gs.n; g += (size_t)gridDim.x * blockDim.x) {
+    const Pos p = load_pos(gs.rec, gs.n, g);
+    gs.keys[g * ((size_t)gs.history_cap + 1)] = position_key(p);
+    gs.plies[g] = 0;
+    gs.perspective[g] = (u8)meta_stm(p.meta);
+    gs.threefold[g] = 0;
+  }
+}
+
+/* Game::apply (game.rs:54-59); action 0xFFFF = leave the game untouched */
+__global__ void __launch_bounds__(FLAT_THREADS) k_games_apply(DeviceTables dt, GamesState gs, const u16* __restrict__ actions) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SharedTables* st = reinterpret_cast<SharedTables*>(smem);
+  stage_tables(st, dt.image);
+  const Tables tb{st, dt.g};
+  for (size_t g = (size_t)blockIdx.x * FLAT_THREADS + threadIdx.x; g < gs.n; g += (size_t)gridDim.x * FLAT_THREADS) {
+    const u16 action = actions[g];
+    if (action == 0xFFFF) continue;
+    const u32 ply = gs.plies[g];
+    if (ply >= gs.history_cap) {
+      atomicAdd(gs.overflow, 1u);
+      continue;
+    }
+    Pos p = load_pos(gs.rec, gs.n, g);
+    make_move(p, tb, action);
+    store_pos(gs.rec, gs.n, g, p);
+    gs.threefold[g] = record_key(gs, g, ply + 1, position_key(p));
+    gs.plies[g] = ply + 1;
+  }
+}
+
+__global__ void __launch_bounds__(FLAT_THREADS) k_games_result(DeviceTables dt, GamesState gs, u8* __restrict__ results) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SharedTables* st = reinterpret_cast<SharedTables*>(smem);
+  stage_tables(st, dt.image);
+  const Tables tb{st, dt.g};
+  for (size_t g = (size_t)blockIdx.x * FLAT_THREADS + threadIdx.x; g < gs.n; g += (size_t)gridDim.x * FLAT_THREADS) {
+    const Pos p = load_pos(gs.rec, gs.n, g);
+    results[g] = (u8)game_result(p, tb, gs.threefold[g] != 0, gs.perspective[g], count_moves(p, tb));
+  }
+}
+
+/* Uniformly random self-play: actions()[splitmix64(seed) % n] until result() is Some or max_plies actions */
+__global__ void __launch_bounds__(FLAT_THREADS)
+k_games_play_random(DeviceTables dt, GamesState gs, const u64* __restrict__ seeds, u32 max_plies, u8* __restrict__ results,
+                    u32* __restrict__ applied) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SharedTables* st = reinterpret_cast<SharedTables*>(smem);
+  stage_tables(st, dt.image);
+  const Tables tb{st, dt.g};
+  for (size_t g = (size_t)blockIdx.x * FLAT_THREADS + threadIdx.x; g < gs.n; g += (size_t)gridDim.x * FLAT_THREADS) {
+    Pos p = load_pos(gs.rec, gs.n, g);
+    u64 seed = seeds[g];
+    u32 ply = gs.plies[g], done = 0;
+    bool threefold = gs.threefold[g] != 0;
+    const int perspective = gs.perspective[g];
+    int r;
+    for (;;) {
+      const u32 n = count_moves(p, tb);
+      r = game_result(p, tb, threefold, perspective, n);
+      if (r != 0 || done >= max_plies) break;
+      if (ply >= gs.history_cap) {
+        atomicAdd(gs.overflow, 1u);
+        break;
+      }
+      const u32 pick = (u32)(splitmix64(seed) % n);
+      u32 k = 0;
+      u16 chosen = 0;
+      generate_moves(p, tb, [&](int from, int to, int promo, int) {
+        if (k++ == pick) chosen = pack_move(from, to, promo);
+      });
+      make_move(p, tb, chosen);
+      threefold = record_key(gs, g, ++ply, position_key(p));
+      ++done;
+    }
+    store_pos(gs.rec, gs.n, g, p);
+    gs.plies[g] = ply;
+    gs.threefold[g] = threefold;
+    results[g] = (u8)r;
+    applied[g] = done;
+  }
+}
+
 /* every shard_count-th record starting at shard_index (root-subtree sharding) */
 __global__ void k_gather_shard(Frontier in, size_t n_out, u32 shard_index, u32 shard_count, Frontier out) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (size_t)gridDim.x * blockDim.x) {

@@ -42,6 +42,11 @@ pub struct Ctx {
     _private: [u8; 0],
 }
 
+#[repr(C)]
+pub struct Games {
+    _private: [u8; 0],
+}
+
 extern "C" {
     pub fn pabi_position_starting(out: *mut RawPosition);
     pub fn pabi_position_from_fen(fen: *const c_char, out: *mut RawPosition, err: *mut c_char, cap: usize) -> i32;
@@ -77,6 +82,15 @@ extern "C" {
                                   children: *mut RawPosition, children_cap: usize, t: *mut Timing) -> i32;
     pub fn pabi_cuda_random_playouts(ctx: *mut Ctx, starts: *const RawPosition, seeds: *const u64, n_games: usize, max_plies: u32,
                                      stride: u32, per_game_cap: u32, out: *mut RawPosition, counts: *mut u32, t: *mut Timing) -> i32;
+    // Game environment (src/chess/game.rs:21-111 without the Syzygy branch); `Games` is an opaque handle like `Ctx`
+    pub fn pabi_cuda_games_create(ctx: *mut Ctx, roots: *const RawPosition, n: usize, history_cap: u32, out: *mut *mut Games) -> i32;
+    pub fn pabi_cuda_games_destroy(games: *mut Games);
+    pub fn pabi_cuda_games_actions(games: *mut Games, offsets: *mut u32, moves: *mut u16, moves_cap: usize) -> i32;
+    pub fn pabi_cuda_games_apply(games: *mut Games, actions: *const u16) -> i32;
+    pub fn pabi_cuda_games_result(games: *mut Games, results: *mut u8) -> i32;
+    pub fn pabi_cuda_games_positions(games: *mut Games, out: *mut RawPosition) -> i32;
+    pub fn pabi_cuda_games_play_random(games: *mut Games, seeds: *const u64, max_plies: u32, results: *mut u8, plies: *mut u32,
+                                       t: *mut Timing) -> i32;
     pub fn pabi_cuda_pack_records(ctx: *mut Ctx, positions: *const RawPosition, n: usize, device_records: *mut u64,
                                   stride: usize) -> i32;
     pub fn pabi_cuda_generate_moves_device(ctx: *mut Ctx, device_records: *const u64, stride: usize, n: usize,

@@ -43,7 +43,7 @@ class AttackInfo(C.Structure):
 
 def build(force: bool = False) -> Path:
     so = ORACLE_DIR / "liboracle.so"
-    srcs = [ORACLE_DIR / f for f in ("tables.c", "position.c", "movegen.c", "drivers.c",
+    srcs = [ORACLE_DIR / f for f in ("tables.c", "position.c", "movegen.c", "drivers.c", "game.c",
                                      "pabi_oracle.h", "oracle_internal.h", "Makefile")]
     if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["make", "-C", str(ORACLE_DIR), "-B" if force else "-s"], check=True,
@@ -88,6 +88,15 @@ def lib() -> C.CDLL:
     L.oracle_generate_moves_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]
     L.oracle_random_playout.restype = C.c_size_t
     L.oracle_random_playout.argtypes = [P, C.c_uint64, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
+    L.oracle_game_new.restype = C.c_void_p
+    L.oracle_game_new.argtypes = [P]
+    L.oracle_game_free.argtypes = [C.c_void_p]
+    L.oracle_game_actions.restype = C.c_uint32
+    L.oracle_game_actions.argtypes = [C.c_void_p, C.POINTER(C.c_uint16)]
+    L.oracle_game_apply.argtypes = [C.c_void_p, C.c_uint16]
+    L.oracle_game_result.argtypes = [C.c_void_p]
+    L.oracle_game_position.argtypes = [C.c_void_p, P]
+    L.oracle_game_play_random.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32)]
     _lib = L
     return L
 
@@ -205,3 +214,39 @@ def random_playout(start: Position, seed: int, max_plies: int, stride: int = 1) 
     arr = np.zeros(cap, dtype=POSITION_DTYPE)
     n = lib().oracle_random_playout(C.byref(start), seed, max_plies, arr.ctypes.data, cap, stride)
     return arr[:n].copy()
+
+
+RESULTS = {0: None, 1: "win", 2: "draw", 3: "loss"}
+
+
+class Game:
+    """pabi's `Game` (game.rs:21-111) without the Syzygy branch, on the CPU oracle."""
+
+    def __init__(self, root: Position):
+        self._g = lib().oracle_game_new(C.byref(root))
+
+    def __del__(self):
+        if getattr(self, "_g", None):
+            lib().oracle_game_free(self._g)
+            self._g = None
+
+    def actions(self) -> list:
+        out = (C.c_uint16 * 256)()
+        n = lib().oracle_game_actions(self._g, out)
+        return list(out[:n])
+
+    def apply(self, move: int) -> None:
+        lib().oracle_game_apply(self._g, move)
+
+    def result(self):
+        return RESULTS[lib().oracle_game_result(self._g)]
+
+    def position(self) -> Position:
+        p = Position()
+        lib().oracle_game_position(self._g, C.byref(p))
+        return p
+
+    def play_random(self, seed: int, max_plies: int):
+        plies = C.c_uint32()
+        r = lib().oracle_game_play_random(self._g, seed, max_plies, C.byref(plies))
+        return RESULTS[r], plies.value

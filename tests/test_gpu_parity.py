@@ -237,6 +237,71 @@ def test_random_playouts_on_device_equal_the_oracle_driver(pb, engine):
         assert total >= 600
 
 
+# ---- Game environment (src/chess/game.rs:21-111 without the Syzygy branch) ----
+
+def test_reference_game_tests(pb, engine):
+    """game.rs:143-227: repetition, stalemate, checkmate, fifty-move rule -- four games in one batch."""
+    fens = ["rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1",
+            "3b2qk/p6p/1p3Q1P/8/8/n7/PP6/K7 b - - 3 2",
+            "3b3k/p5qp/1p3Q1P/8/8/n7/PP6/K7 w - - 4 3",
+            "8/5k2/3p4/1p1Pp2p/pP2Pp1P/P4P1K/8/8 b - - 99 50"]
+    games = pb.Games(engine, [pb.Position.from_fen(f) for f in fens], history_cap=16)
+    assert games.result() == [None, None, None, None]
+    games.apply([pb.Move.from_uci("g1f3"), pb.Move.from_uci("d8f6"), pb.Move.from_uci("f6g7"), pb.Move.from_uci("f7f6")])
+    assert games.result() == [None, "draw", "win", "draw"]
+    offsets, moves = games.actions()
+    assert offsets[2] - offsets[1] == 0 and offsets[3] - offsets[2] == 0      # stalemate and checkmate: no actions
+    for i, u in enumerate(["g8f6", "f3g1", "f6g8", "g1f3", "g8f6", "f3g1"]):
+        games.apply([pb.Move.from_uci(u), None, None, None])
+        assert games.result()[0] is None, i
+    games.apply([pb.Move.from_uci("f6g8"), None, None, None])
+    assert games.result() == ["draw", "draw", "win", "draw"]                  # threefold repetition
+    assert str(pb.Position.from_record(games.positions()[0])).startswith("rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq -")
+    with pytest.raises(pb.PabiCudaError):                                     # history_cap = 16 actions
+        for _ in range(12):
+            games.apply([pb.Move.from_uci("g1f3"), None, None, None])
+            games.apply([pb.Move.from_uci("g8f6"), None, None, None])
+            games.apply([pb.Move.from_uci("f3g1"), None, None, None])
+            games.apply([pb.Move.from_uci("f6g8"), None, None, None])
+    games.close()
+
+
+def test_repetition_semantics_follow_the_reference(pb, engine):
+    """tests/test_oracle_game.py::test_repetition_key_ignores_the_side_to_move_like_the_reference on the device."""
+    from test_oracle_game import TRIANGULATION
+    games = pb.Games(engine, [pb.Position.from_fen("8/8/8/3k4/8/3K4/8/8 w - - 0 1")], history_cap=32)
+    for u in TRIANGULATION[:-1]:
+        games.apply([pb.Move.from_uci(u)])
+        assert games.result() == [None]
+    games.apply([pb.Move.from_uci(TRIANGULATION[-1])])
+    assert games.result() == ["draw"]
+    games.close()
+
+
+def test_random_self_play_equals_the_oracle_game(pb, engine):
+    """Whole games on the device: result, length and final position of every game equal the CPU `Game`."""
+    import workloads
+    fens = workloads.chess324_fens()
+    roots = [oracle.starting() if g % 3 else oracle.parse(fens[g % 324]) for g in range(1500)]
+    roots += [oracle.from_fen("8/5k2/3p4/1p1Pp2p/pP2Pp1P/P4P1K/8/8 b - - 90 50"), oracle.from_fen("4k3/8/8/8/8/8/8/R3K3 w Q - 0 1")] * 20
+    seeds = [0x6A3E0000 + g for g in range(len(roots))]
+    games = pb.Games(engine, oracle.positions_array(roots), history_cap=700)
+    results, plies = games.play_random(seeds, 600)
+    finals = games.positions()
+    tally = {}
+    for g, root in enumerate(roots):
+        og = oracle.Game(root)
+        r, n = og.play_random(seeds[g], 600)
+        assert (results[g], int(plies[g])) == (r, n), g
+        want = og.position()
+        want.hash = 0
+        assert bytes(want) == finals[g].tobytes(), g
+        tally[r] = tally.get(r, 0) + 1
+    assert tally.get("draw", 0) > 0 and (tally.get("win", 0) + tally.get("loss", 0)) > 0
+    assert games.result() == results                                          # Game::result agrees after the fact
+    games.close()
+
+
 # ---- text API through the same library (tests/chess.rs:33-181) ----
 
 def test_fen_round_trips_and_errors(pb, vectors):
