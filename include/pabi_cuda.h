@@ -60,6 +60,7 @@ typedef struct {
   uint64_t leaf_kernel_launches;
   uint64_t leaf_parents;      /* records it read from HBM (ply depth-2) */
   uint64_t leaf_children;     /* positions it generated, counted and never wrote out (ply depth-1) */
+  uint64_t merged_records;    /* pabi_cuda_perft_hashed: frontier records removed by transposition merging */
 } pabi_timing_t;
 
 /* ---- host-side text API (no device work) -------------------------------- */
@@ -86,6 +87,14 @@ int pabi_cuda_device(const pabi_cuda_ctx* ctx);
 /* perft(&Position, depth), src/chess/position.rs:909-924 */
 int pabi_cuda_perft(pabi_cuda_ctx* ctx, const pabi_position_t* root, uint8_t depth, uint64_t* nodes,
                     pabi_timing_t* timing);
+/* perft with transposition merging ("hashed perft"): after every breadth-first ply the
+ * records that are the same position (placement, side to move, castling rights, en passant square) are
+ * merged into one record that carries the number of paths reaching it, so shared subtrees are walked
+ * once.  Candidates are grouped by a 64-bit tag and then compared in full, so the result is exactly
+ * perft(root, depth); only the work changes.  The reference has no such mode (its perft is the plain
+ * recursion); throughput of this entry point is "effective" nodes/s and is never what bench.py reports. */
+int pabi_cuda_perft_hashed(pabi_cuda_ctx* ctx, const pabi_position_t* root, uint8_t depth, uint64_t* nodes,
+                           pabi_timing_t* timing);
 /* The same for n independent roots in one pass (benches/chess.rs:49-104 loops over
  * positions; tests/chess.rs:555-578 loops over a book): nodes_out[i] = perft(roots[i], depth). */
 int pabi_cuda_perft_batch(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, uint8_t depth,

@@ -54,13 +54,15 @@ class Timing(C.Structure):
         ("leaf_kernel_launches", C.c_uint64),
         ("leaf_parents", C.c_uint64),
         ("leaf_children", C.c_uint64),
+        ("merged_records", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:
         return {"device_ms": self.device_ms, "host_ms": self.host_ms, "algorithmic_bytes": self.algorithmic_bytes,
                 "kernel_launches": self.kernel_launches, "interior_nodes": self.interior_nodes,
                 "leaf_kernel_ms": self.leaf_kernel_ms, "leaf_kernel_launches": self.leaf_kernel_launches,
-                "leaf_parents": self.leaf_parents, "leaf_children": self.leaf_children}
+                "leaf_parents": self.leaf_parents, "leaf_children": self.leaf_children,
+                "merged_records": self.merged_records}
 
 
 class PabiCudaError(RuntimeError):
@@ -74,7 +76,7 @@ class PabiCudaError(RuntimeError):
 EXPORTS = (
     "pabi_position_starting", "pabi_position_from_fen", "pabi_position_parse", "pabi_position_to_fen",
     "pabi_move_from_uci", "pabi_move_to_uci", "pabi_cuda_create", "pabi_cuda_destroy", "pabi_cuda_last_error",
-    "pabi_cuda_device", "pabi_cuda_perft", "pabi_cuda_perft_batch", "pabi_cuda_perft_shard", "pabi_cuda_perft_multi", "pabi_cuda_perft_divide",
+    "pabi_cuda_device", "pabi_cuda_perft", "pabi_cuda_perft_hashed", "pabi_cuda_perft_batch", "pabi_cuda_perft_shard", "pabi_cuda_perft_multi", "pabi_cuda_perft_divide",
     "pabi_cuda_generate_moves_batch", "pabi_cuda_count_moves_batch", "pabi_cuda_in_check_batch",
     "pabi_cuda_attack_info_batch", "pabi_cuda_make_moves_batch", "pabi_cuda_expand_batch", "pabi_cuda_pack_records",
     "pabi_cuda_generate_moves_device", "pabi_cuda_random_playouts",
@@ -116,6 +118,7 @@ def lib() -> C.CDLL:
     L.pabi_cuda_last_error.restype = C.c_char_p
     L.pabi_cuda_device.argtypes = [vp]
     L.pabi_cuda_perft.argtypes = [vp, P, u8, u64p, T]
+    L.pabi_cuda_perft_hashed.argtypes = [vp, P, u8, u64p, T]
     L.pabi_cuda_perft_batch.argtypes = [vp, vp, sz, u8, vp, T]
     L.pabi_cuda_perft_shard.argtypes = [vp, P, u8, u32, u32, u32, u64p, T]
     L.pabi_cuda_perft_multi.argtypes = [C.POINTER(vp), sz, P, u8, u32, u64p, C.POINTER(C.c_double)]

@@ -122,6 +122,13 @@ class Engine:
         self.last_timing = t
         return nodes.value
 
+    def perft_hashed(self, position: "Position", depth: int) -> int:
+        """perft with transposition merging (`pabi_cuda_perft_hashed`): same result, shared subtrees walked once."""
+        nodes, t = C.c_uint64(), Timing()
+        self._check(_native.lib().pabi_cuda_perft_hashed(self._ctx, C.byref(position.raw), depth, C.byref(nodes), C.byref(t)))
+        self.last_timing = t
+        return nodes.value
+
     def perft_batch(self, positions, depth: int) -> np.ndarray:
         arr = _as_array(positions)
         out, t = np.zeros(len(arr), dtype=np.uint64), Timing()

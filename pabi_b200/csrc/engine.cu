@@ -38,6 +38,7 @@ struct Level {
   u32* roots = nullptr;
   u32* counts = nullptr;
   u64* prefix = nullptr;
+  u64* mult = nullptr; /* only for perft with transposition merging */
   size_t cap = 0;
 };
 
@@ -60,6 +61,11 @@ struct pabi_cuda_ctx {
   u64* d_rays = nullptr;
   Level levels[MAX_LEVELS];
   Level spare; /* shard gather target */
+  Level merge_level; /* compaction target of merge_transpositions */
+  unsigned long long* d_tags = nullptr;
+  u32* d_owner = nullptr;
+  size_t merge_table = 0;
+  uint64_t merged_away = 0; /* per call: records removed by transposition merging */
   u64* d_tile_sums = nullptr;
   size_t tile_sums_cap = 0;
   u64* d_result = nullptr; /* {end, children} of k_chunk_end */
@@ -117,7 +123,7 @@ void* ensure(pabi_cuda_ctx* ctx, int slot, size_t bytes) {
 
 void alloc_level(pabi_cuda_ctx* ctx, Level& l, size_t cap) {
   if (l.cap >= cap) return;
-  if (l.rec) cudaFree(l.rec), cudaFree(l.roots), cudaFree(l.counts), cudaFree(l.prefix);
+  if (l.rec) cudaFree(l.rec), cudaFree(l.roots), cudaFree(l.counts), cudaFree(l.prefix), cudaFree(l.mult);
   l = Level();
   CK(cudaMalloc(&l.rec, cap * POS_WORDS * sizeof(u64)));
   CK(cudaMalloc(&l.roots, cap * sizeof(u32)));
@@ -126,7 +132,11 @@ void alloc_level(pabi_cuda_ctx* ctx, Level& l, size_t cap) {
   l.cap = cap;
 }
 
-Frontier frontier_of(const Level& l) { return Frontier{l.rec, l.roots, l.cap}; }
+Frontier frontier_of(const Level& l) { return Frontier{l.rec, l.roots, l.cap, l.mult}; }
+
+void ensure_mult(pabi_cuda_ctx* ctx, Level& l) {
+  if (!l.mult) CK(cudaMalloc(&l.mult, l.cap * sizeof(u64)));
+}
 
 void ensure_nodes(pabi_cuda_ctx* ctx, size_t n) {
   if (ctx->nodes_cap >= n) return;
@@ -150,10 +160,17 @@ using TileV4 = TileConfig<1024, 128, 3072, 1, 8>;
 using TileV5 = TileConfig<768, 256, 6144, 1, 3>;
 constexpr int TILE_VARIANTS = 6;
 
+/* prefix[0..n] = exclusive scan of counts[0..n) */
+void scan_counts(pabi_cuda_ctx* ctx, const u32* counts, size_t n, u64* prefix);
+
 /* counts[0..n) of records [first, first+n) of `l`, then prefix[0..n] */
 void count_and_scan(pabi_cuda_ctx* ctx, const u64* rec, size_t stride, size_t first, size_t n, u32* counts, u64* prefix) {
   k_count<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, rec, stride, first, n, counts);
   LAUNCHED();
+  scan_counts(ctx, counts, n, prefix);
+}
+
+void scan_counts(pabi_cuda_ctx* ctx, const u32* counts, size_t n, u64* prefix) {
   const size_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   if (ctx->tile_sums_cap < tiles) {
     if (ctx->d_tile_sums) CK(cudaFree(ctx->d_tile_sums));
@@ -169,37 +186,39 @@ void count_and_scan(pabi_cuda_ctx* ctx, const u64* rec, size_t stride, size_t fi
   LAUNCHED();
 }
 
-template <TileMode MODE, bool MULTI, class CFG>
+template <TileMode MODE, Accounting ACC, class CFG>
 void launch_tile_cfg(pabi_cuda_ctx* ctx, Frontier in, size_t first, size_t n, const u64* prefix, TileOut out) {
   static bool configured[8] = {};
   if (!configured[ctx->device & 7]) { /* the table image alone exceeds the default 48 KB of dynamic shared memory */
-    CK(cudaFuncSetAttribute(k_tile<MODE, MULTI, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared<CFG>)));
+    CK(cudaFuncSetAttribute(k_tile<MODE, ACC, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared<CFG>)));
     configured[ctx->device & 7] = true;
   }
   const int grid = grid_for(ctx, n, CFG::PARENTS, CFG::MIN_BLOCKS);
-  k_tile<MODE, MULTI, CFG><<<grid, CFG::THREADS, sizeof(TileShared<CFG>), ctx->stream>>>(ctx->dt, in, first, n, prefix, out);
+  k_tile<MODE, ACC, CFG><<<grid, CFG::THREADS, sizeof(TileShared<CFG>), ctx->stream>>>(ctx->dt, in, first, n, prefix, out);
   LAUNCHED();
 }
 
 /* K2: the last two plies below the n records of `in` */
-void launch_leaf(pabi_cuda_ctx* ctx, bool multi, Frontier in, size_t n) {
+void launch_leaf(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n) {
   while (ctx->leaf_events.size() < 2 * (ctx->leaf_launches + 1)) {
     cudaEvent_t e;
     CK(cudaEventCreate(&e));
     ctx->leaf_events.push_back(e);
   }
   CK(cudaEventRecord(ctx->leaf_events[2 * ctx->leaf_launches], ctx->stream));
-  const TileOut out{Frontier{nullptr, nullptr, 0}, nullptr, nullptr, ctx->d_nodes, ctx->d_visited};
-  if (multi) {
-    launch_tile_cfg<TILE_LEAF, true, TileDefault>(ctx, in, 0, n, nullptr, out);
+  const TileOut out{Frontier{nullptr, nullptr, 0, nullptr}, nullptr, nullptr, ctx->d_nodes, ctx->d_visited};
+  if (acc == PER_ROOT) {
+    launch_tile_cfg<TILE_LEAF, PER_ROOT, TileDefault>(ctx, in, 0, n, nullptr, out);
+  } else if (acc == WEIGHTED) {
+    launch_tile_cfg<TILE_LEAF, WEIGHTED, TileDefault>(ctx, in, 0, n, nullptr, out);
   } else {
     switch (ctx->tile_variant) {
-      case 1: launch_tile_cfg<TILE_LEAF, false, TileV1>(ctx, in, 0, n, nullptr, out); break;
-      case 2: launch_tile_cfg<TILE_LEAF, false, TileV2>(ctx, in, 0, n, nullptr, out); break;
-      case 3: launch_tile_cfg<TILE_LEAF, false, TileV3>(ctx, in, 0, n, nullptr, out); break;
-      case 4: launch_tile_cfg<TILE_LEAF, false, TileV4>(ctx, in, 0, n, nullptr, out); break;
-      case 5: launch_tile_cfg<TILE_LEAF, false, TileV5>(ctx, in, 0, n, nullptr, out); break;
-      default: launch_tile_cfg<TILE_LEAF, false, TileDefault>(ctx, in, 0, n, nullptr, out); break;
+      case 1: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV1>(ctx, in, 0, n, nullptr, out); break;
+      case 2: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV2>(ctx, in, 0, n, nullptr, out); break;
+      case 3: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV3>(ctx, in, 0, n, nullptr, out); break;
+      case 4: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV4>(ctx, in, 0, n, nullptr, out); break;
+      case 5: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV5>(ctx, in, 0, n, nullptr, out); break;
+      default: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileDefault>(ctx, in, 0, n, nullptr, out); break;
     }
   }
   CK(cudaEventRecord(ctx->leaf_events[2 * ctx->leaf_launches + 1], ctx->stream));
@@ -208,35 +227,80 @@ void launch_leaf(pabi_cuda_ctx* ctx, bool multi, Frontier in, size_t n) {
 }
 
 /* K1: children of records [first, first + n) of `in`, at the offsets of `prefix` (count_and_scan) */
-void launch_expand(pabi_cuda_ctx* ctx, bool multi, Frontier in, size_t first, size_t n, const u64* prefix, Frontier children) {
+void launch_expand(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t first, size_t n, const u64* prefix, Frontier children) {
   const TileOut out{children, nullptr, nullptr, nullptr, nullptr};
-  if (multi) launch_tile_cfg<TILE_EXPAND, true, TileDefault>(ctx, in, first, n, prefix, out);
-  else launch_tile_cfg<TILE_EXPAND, false, TileDefault>(ctx, in, first, n, prefix, out);
+  if (acc == PER_ROOT) launch_tile_cfg<TILE_EXPAND, PER_ROOT, TileDefault>(ctx, in, first, n, prefix, out);
+  else if (acc == WEIGHTED) launch_tile_cfg<TILE_EXPAND, WEIGHTED, TileDefault>(ctx, in, first, n, prefix, out);
+  else launch_tile_cfg<TILE_EXPAND, SINGLE_ROOT, TileDefault>(ctx, in, first, n, prefix, out);
 }
 
 /* K3: ordered move lists of records [0, n) at the offsets of `prefix`; the caller has checked the capacity */
 void launch_moves(pabi_cuda_ctx* ctx, const u64* rec, size_t stride, size_t n, const u64* prefix, u16* moves, u32* offsets) {
-  const TileOut out{Frontier{nullptr, nullptr, 0}, moves, offsets, nullptr, nullptr};
-  launch_tile_cfg<TILE_MOVES, false, TileDefault>(ctx, Frontier{const_cast<u64*>(rec), nullptr, stride}, 0, n, prefix, out);
+  const TileOut out{Frontier{nullptr, nullptr, 0, nullptr}, moves, offsets, nullptr, nullptr};
+  launch_tile_cfg<TILE_MOVES, SINGLE_ROOT, TileDefault>(ctx, Frontier{const_cast<u64*>(rec), nullptr, stride, nullptr}, 0, n, prefix, out);
 }
 
 /* Walks `remaining` plies below the n records of level `lv`, adding leaf counts
  * to d_nodes (per root when multi). */
-void descend(pabi_cuda_ctx* ctx, int lv, size_t n, int remaining, bool multi) {
-  if (n == 0) return;
+/* Transposition merging of the n records of level `lv` (WEIGHTED accounting): identical positions
+ * are merged and their multiplicities summed.  Returns the number of survivors, which replace the
+ * level's contents (compacted through ctx->merge_level). */
+size_t merge_transpositions(pabi_cuda_ctx* ctx, int lv, size_t n) {
+  if (n < 2) return n;
   Level& cur = ctx->levels[lv];
+  size_t table = 1;
+  while (table < 2 * n) table <<= 1;
+  if (ctx->merge_table < table) {
+    if (ctx->d_tags) {
+      CK(cudaFree(ctx->d_tags));
+      CK(cudaFree(ctx->d_owner));
+    }
+    ctx->d_tags = nullptr, ctx->d_owner = nullptr, ctx->merge_table = 0;
+    CK(cudaMalloc(&ctx->d_tags, table * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->d_owner, table * sizeof(u32)));
+    ctx->merge_table = table;
+  }
+  u32* slot_of = (u32*)ensure(ctx, 4, n * sizeof(u32));
+  alloc_level(ctx, ctx->merge_level, cur.cap);
+  ensure_mult(ctx, ctx->merge_level);
+  CK(cudaMemsetAsync(ctx->d_tags, 0, table * sizeof(unsigned long long), ctx->stream));
+  const int grid = grid_for(ctx, n, 256, 8);
+  k_dedup_insert<<<grid, 256, 0, ctx->stream>>>(cur.rec, cur.cap, n, ctx->d_tags, table - 1, ctx->d_owner, slot_of, cur.counts);
+  LAUNCHED();
+  k_dedup_verify<<<grid, 256, 0, ctx->stream>>>(cur.rec, cur.cap, n, ctx->d_owner, slot_of, cur.counts,
+                                               (unsigned long long*)cur.mult);
+  LAUNCHED();
+  scan_counts(ctx, cur.counts, n, cur.prefix); /* counts = survivor flags */
+  k_dedup_compact<<<grid, 256, 0, ctx->stream>>>(cur.rec, cur.cap, n, cur.counts, cur.prefix, cur.mult, ctx->merge_level.rec,
+                                                ctx->merge_level.cap, ctx->merge_level.mult);
+  LAUNCHED();
+  CK(cudaMemcpyAsync(ctx->h_result, cur.prefix + n, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::swap(ctx->levels[lv], ctx->merge_level);
+  ctx->merged_away += n - (size_t)ctx->h_result[0];
+  return (size_t)ctx->h_result[0];
+}
+
+/* Walks `remaining` plies below the n records of level `lv`, adding leaf counts
+ * to d_nodes (per root for PER_ROOT; times the record's multiplicity for WEIGHTED, where every
+ * expanded chunk is passed through merge_transpositions). */
+void descend(pabi_cuda_ctx* ctx, int lv, size_t n, int remaining, Accounting acc) {
+  if (n == 0) return;
   ctx->interior += n;
   if (remaining == 1) {
+    Level& cur = ctx->levels[lv];
     const int grid = grid_for(ctx, n, FLAT_THREADS, 4);
-    if (multi)
-      k_count_accumulate<true><<<grid, FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, frontier_of(cur), n, ctx->d_nodes);
+    if (acc == PER_ROOT)
+      k_count_accumulate<PER_ROOT><<<grid, FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, frontier_of(cur), n, ctx->d_nodes);
+    else if (acc == WEIGHTED)
+      k_count_accumulate<WEIGHTED><<<grid, FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, frontier_of(cur), n, ctx->d_nodes);
     else
-      k_count_accumulate<false><<<grid, FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, frontier_of(cur), n, ctx->d_nodes);
+      k_count_accumulate<SINGLE_ROOT><<<grid, FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, frontier_of(cur), n, ctx->d_nodes);
     LAUNCHED();
     return;
   }
   if (remaining == 2) {
-    launch_leaf(ctx, multi, frontier_of(cur), n);
+    launch_leaf(ctx, acc, frontier_of(ctx->levels[lv]), n);
     /* the children are generated and counted inside the kernel */
     return;
   }
@@ -244,24 +308,31 @@ void descend(pabi_cuda_ctx* ctx, int lv, size_t n, int remaining, bool multi) {
     ctx->error = "perft depth exceeds the supported number of breadth-first levels";
     throw CudaFail{cudaErrorInvalidValue};
   }
-  Level& next = ctx->levels[lv + 1];
-  alloc_level(ctx, next, ctx->capacity);
-  count_and_scan(ctx, cur.rec, cur.cap, 0, n, cur.counts, cur.prefix);
+  alloc_level(ctx, ctx->levels[lv + 1], ctx->capacity);
+  if (acc == WEIGHTED) ensure_mult(ctx, ctx->levels[lv + 1]);
+  {
+    Level& cur = ctx->levels[lv];
+    count_and_scan(ctx, cur.rec, cur.cap, 0, n, cur.counts, cur.prefix);
+  }
   size_t start = 0;
   while (start < n) {
+    /* levels may have been swapped by a deeper merge_transpositions: re-read them every time */
+    Level& cur = ctx->levels[lv];
+    Level& next = ctx->levels[lv + 1];
     k_chunk_end<<<1, 1, 0, ctx->stream>>>(cur.prefix, start, n, (u64)next.cap, ctx->d_result);
     LAUNCHED();
     CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result, 2 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const size_t end = (size_t)ctx->h_result[0];
-    const size_t children = (size_t)ctx->h_result[1];
+    size_t children = (size_t)ctx->h_result[1];
     if (end == start) {
       ctx->error = "frontier capacity is smaller than one position's move list";
       throw CudaFail{cudaErrorInvalidValue};
     }
     if (children) {
-      launch_expand(ctx, multi, frontier_of(cur), start, end - start, cur.prefix, frontier_of(next));
-      descend(ctx, lv + 1, children, remaining - 1, multi);
+      launch_expand(ctx, acc, frontier_of(cur), start, end - start, cur.prefix, frontier_of(next));
+      if (acc == WEIGHTED) children = merge_transpositions(ctx, lv + 1, children);
+      descend(ctx, lv + 1, children, remaining - 1, acc);
     }
     start = end;
   }
@@ -317,8 +388,9 @@ int bad_arg(pabi_cuda_ctx* ctx, const char* what) {
   return -1;
 }
 
-int perft_impl(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, int depth, uint64_t* nodes_out, bool multi,
+int perft_impl(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, int depth, uint64_t* nodes_out, Accounting acc,
                uint32_t split_ply, uint32_t shard_index, uint32_t shard_count, pabi_timing_t* timing) {
+  const bool multi = acc == PER_ROOT;
   try {
     CK(cudaSetDevice(ctx->device));
     CallTimer timer(ctx);
@@ -331,11 +403,17 @@ int perft_impl(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, int d
     const size_t n_out = multi ? n : 1;
     ensure_nodes(ctx, n_out);
     upload_roots(ctx, roots, n);
+    ctx->merged_away = 0;
+    if (acc == WEIGHTED) { /* the root is reached by one path */
+      ensure_mult(ctx, ctx->levels[0]);
+      const u64 one = 1;
+      CK(cudaMemcpyAsync(ctx->levels[0].mult, &one, sizeof one, cudaMemcpyHostToDevice, ctx->stream));
+    }
     timer.begin_device();
     CK(cudaMemsetAsync(ctx->d_nodes, 0, n_out * sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_visited, 0, sizeof(unsigned long long), ctx->stream));
     if (shard_count <= 1) {
-      descend(ctx, 0, n, depth, multi);
+      descend(ctx, 0, n, depth, acc);
     } else {
       /* breadth-first to the split ply (at most depth - 1 so that one ply is left), whole levels only */
       int remaining = depth;
@@ -355,7 +433,7 @@ int perft_impl(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, int d
           throw CudaFail{cudaErrorInvalidValue};
         }
         alloc_level(ctx, next, ctx->capacity);
-        if (children) launch_expand(ctx, multi, frontier_of(cur), 0, cnt, cur.prefix, frontier_of(next));
+        if (children) launch_expand(ctx, acc, frontier_of(cur), 0, cnt, cur.prefix, frontier_of(next));
         ctx->interior += cnt;
         cnt = children, ++lv, --remaining;
       }
@@ -367,7 +445,7 @@ int perft_impl(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, int d
                                                                             shard_count, frontier_of(ctx->spare));
         LAUNCHED();
         std::swap(ctx->levels[lv], ctx->spare);
-        descend(ctx, lv, mine, remaining, multi);
+        descend(ctx, lv, mine, remaining, acc);
       }
     }
     timer.end_device();
@@ -377,7 +455,7 @@ int perft_impl(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, int d
     ctx->interior += ctx->h_result[2];
     /* every node of plies 1..d-1 written once and read once at 64 B */
     timer.finish(timing, 2 * 64 * (ctx->interior > n ? ctx->interior - n : 0));
-    if (timing) timing->leaf_children = ctx->h_result[2];
+    if (timing) timing->leaf_children = ctx->h_result[2], timing->merged_records = ctx->merged_away;
     return 0;
   } catch (const CudaFail& f) {
     return fail(ctx, f);
@@ -422,8 +500,9 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     CK(cudaMallocHost(&ctx->h_result, 4 * sizeof(u64)));
     /* kernels that stage the table image need more than the default 48 KB of dynamic shared memory */
     CK(cudaFuncSetAttribute(k_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
-    CK(cudaFuncSetAttribute(k_count_accumulate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
-    CK(cudaFuncSetAttribute(k_count_accumulate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_count_accumulate<SINGLE_ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_count_accumulate<PER_ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_count_accumulate<WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_in_check, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_attack_info, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_make_moves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
@@ -450,11 +529,13 @@ void pabi_cuda_destroy(pabi_cuda_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   auto free_level = [](Level& l) {
-    if (l.rec) cudaFree(l.rec), cudaFree(l.roots), cudaFree(l.counts), cudaFree(l.prefix);
+    if (l.rec) cudaFree(l.rec), cudaFree(l.roots), cudaFree(l.counts), cudaFree(l.prefix), cudaFree(l.mult);
     l = Level();
   };
   for (Level& l : ctx->levels) free_level(l);
   free_level(ctx->spare);
+  free_level(ctx->merge_level);
+  if (ctx->d_tags) cudaFree(ctx->d_tags), cudaFree(ctx->d_owner);
   for (Buffer& b : ctx->scratch)
     if (b.ptr) cudaFree(b.ptr);
   if (ctx->d_tile_sums) cudaFree(ctx->d_tile_sums);
@@ -477,7 +558,12 @@ int pabi_cuda_device(const pabi_cuda_ctx* ctx) { return ctx ? ctx->device : -1; 
 
 int pabi_cuda_perft(pabi_cuda_ctx* ctx, const pabi_position_t* root, uint8_t depth, uint64_t* nodes, pabi_timing_t* timing) {
   if (!ctx || !root || !nodes) return bad_arg(ctx, "null argument");
-  return perft_impl(ctx, root, 1, depth, nodes, false, 0, 0, 1, timing);
+  return perft_impl(ctx, root, 1, depth, nodes, SINGLE_ROOT, 0, 0, 1, timing);
+}
+
+int pabi_cuda_perft_hashed(pabi_cuda_ctx* ctx, const pabi_position_t* root, uint8_t depth, uint64_t* nodes, pabi_timing_t* timing) {
+  if (!ctx || !root || !nodes) return bad_arg(ctx, "null argument");
+  return perft_impl(ctx, root, 1, depth, nodes, WEIGHTED, 0, 0, 1, timing);
 }
 
 int pabi_cuda_perft_batch(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, uint8_t depth, uint64_t* nodes_out,
@@ -488,14 +574,14 @@ int pabi_cuda_perft_batch(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size
     return 0;
   }
   if (n > ctx->capacity) return bad_arg(ctx, "more roots than the frontier capacity");
-  return perft_impl(ctx, roots, n, depth, nodes_out, true, 0, 0, 1, timing);
+  return perft_impl(ctx, roots, n, depth, nodes_out, PER_ROOT, 0, 0, 1, timing);
 }
 
 int pabi_cuda_perft_shard(pabi_cuda_ctx* ctx, const pabi_position_t* root, uint8_t depth, uint32_t split_ply,
                           uint32_t shard_index, uint32_t shard_count, uint64_t* nodes, pabi_timing_t* timing) {
   if (!ctx || !root || !nodes) return bad_arg(ctx, "null argument");
   if (shard_count == 0 || shard_index >= shard_count) return bad_arg(ctx, "shard_index must be < shard_count");
-  return perft_impl(ctx, root, 1, depth, nodes, false, split_ply, shard_index, shard_count, timing);
+  return perft_impl(ctx, root, 1, depth, nodes, SINGLE_ROOT, split_ply, shard_index, shard_count, timing);
 }
 
 int pabi_cuda_perft_multi(pabi_cuda_ctx* const* ctxs, size_t n_ctx, const pabi_position_t* root, uint8_t depth,
@@ -952,7 +1038,7 @@ int pabi_cuda_expand_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions,
       if (total > ctx->capacity) return bad_arg(ctx, "children exceed the frontier capacity");
       Level& l1 = ctx->levels[1];
       alloc_level(ctx, l1, ctx->capacity);
-      launch_expand(ctx, true, frontier_of(l0), 0, n, l0.prefix, frontier_of(l1));
+      launch_expand(ctx, PER_ROOT, frontier_of(l0), 0, n, l0.prefix, frontier_of(l1));
       PositionImage* d_out = (PositionImage*)ensure(ctx, 3, total * sizeof(PositionImage));
       k_unpack<<<grid_for(ctx, total, 256, 8), 256, 0, ctx->stream>>>(l1.rec, l1.cap, total, d_out);
       LAUNCHED();

@@ -62,6 +62,14 @@ struct Frontier {
   u64* rec;
   u32* roots; /* root index of each record (perft_batch), may be null when single-root */
   size_t stride;
+  u64* mult;  /* WEIGHTED accounting (perft with transposition merging): how many paths reach the record */
+};
+
+/* How leaf counts are attributed */
+enum Accounting {
+  SINGLE_ROOT, /* one total */
+  PER_ROOT,    /* nodes[root of the record] */
+  WEIGHTED     /* one total, every record counted `mult` times */
 };
 
 /* ---- block-wide helpers -------------------------------------------------- */
@@ -141,9 +149,10 @@ k_count(DeviceTables dt, const u64* __restrict__ rec, size_t stride, size_t firs
 }
 
 /* perft with one ply left: nodes[root] += generate_moves().len() (position.rs:914-916) */
-template <bool MULTI_ROOT>
+template <Accounting ACC>
 __global__ void __launch_bounds__(FLAT_THREADS)
 k_count_accumulate(DeviceTables dt, Frontier f, size_t n, unsigned long long* __restrict__ nodes) {
+  constexpr bool MULTI_ROOT = ACC == PER_ROOT;
   extern __shared__ __align__(16) unsigned char smem[];
   SharedTables* st = reinterpret_cast<SharedTables*>(smem);
   __shared__ u64 red[FLAT_THREADS / 32];
@@ -155,7 +164,7 @@ k_count_accumulate(DeviceTables dt, Frontier f, size_t n, unsigned long long* __
     if (MULTI_ROOT) {
       if (c) atomicAdd(nodes + f.roots[i], (unsigned long long)c);
     } else {
-      acc += c;
+      acc += ACC == WEIGHTED ? c * f.mult[i] : (u64)c;
     }
   }
   if (!MULTI_ROOT) block_add_u64<FLAT_THREADS>(acc, red, nodes);
@@ -546,6 +555,71 @@ __global__ void k_chunk_end(const u64* __restrict__ prefix, size_t start, size_t
   result[1] = prefix[lo] - base;
 }
 
+/* ---- transposition merging (perft "with hashing", made exact) -------------------------------
+ * Records of one ply that are the same position (placement, side to move, castling rights, en
+ * passant square; the clocks do not influence perft) are merged into one record whose multiplicity
+ * is the sum.  A 64-bit tag table groups candidates; k_dedup_verify then compares the full records,
+ * so a tag collision between different positions costs a missed merge, never a wrong count. */
+PB_HD u64 dedup_tag(const Pos& p) {
+  u64 h = 0x9E3779B97F4A7C15ULL;
+  const u64 words[8] = {p.white, p.pawns, p.knights, p.bishops, p.rooks, p.queens, p.kings, p.meta & 0xFFFULL};
+  for (int i = 0; i < 8; i++) {
+    h = (h ^ words[i]) * 0xBF58476D1CE4E5B9ULL;
+    h ^= h >> 29;
+  }
+  h *= 0x94D049BB133111EBULL;
+  return (h ^ (h >> 32)) | 1; /* 0 marks an empty slot */
+}
+
+/* open addressing on the tag; the thread that claims a slot becomes the group's owner */
+__global__ void k_dedup_insert(const u64* __restrict__ rec, size_t stride, size_t n, unsigned long long* __restrict__ tags, size_t mask,
+                               u32* __restrict__ owner, u32* __restrict__ slot_of, u32* __restrict__ winner) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const u64 tag = dedup_tag(load_pos(rec, stride, i));
+    size_t slot = (size_t)(tag >> 1) & mask;
+    for (;;) {
+      const unsigned long long old = atomicCAS(tags + slot, 0ULL, (unsigned long long)tag);
+      if (old == 0ULL) {
+        owner[slot] = (u32)i;
+        winner[i] = 1;
+        break;
+      }
+      if (old == tag) {
+        winner[i] = 0;
+        break;
+      }
+      slot = (slot + 1) & mask;
+    }
+    slot_of[i] = (u32)slot;
+  }
+}
+
+/* every non-owner compares itself with its group's owner: equal -> its multiplicity moves to the owner */
+__global__ void k_dedup_verify(const u64* __restrict__ rec, size_t stride, size_t n, const u32* __restrict__ owner,
+                               const u32* __restrict__ slot_of, u32* __restrict__ winner, unsigned long long* __restrict__ mult) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (winner[i]) continue;
+    const size_t j = owner[slot_of[i]];
+    const Pos a = load_pos(rec, stride, i), b = load_pos(rec, stride, j);
+    const bool same = a.white == b.white && a.pawns == b.pawns && a.knights == b.knights && a.bishops == b.bishops &&
+                      a.rooks == b.rooks && a.queens == b.queens && a.kings == b.kings && ((a.meta ^ b.meta) & 0xFFFULL) == 0;
+    if (same) atomicAdd(mult + j, mult[i]);
+    else winner[i] = 1; /* different positions with one tag: keep both */
+  }
+}
+
+/* survivors move to out[prefix[i]] with their accumulated multiplicity */
+__global__ void k_dedup_compact(const u64* __restrict__ rec, size_t stride, size_t n, const u32* __restrict__ winner,
+                                const u64* __restrict__ prefix, const u64* __restrict__ mult, u64* __restrict__ out_rec,
+                                size_t out_stride, u64* __restrict__ out_mult) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (!winner[i]) continue;
+    const size_t o = (size_t)prefix[i];
+    store_pos(out_rec, out_stride, o, load_pos(rec, stride, i));
+    out_mult[o] = mult[i];
+  }
+}
+
 /* ---- K1 / K2: tile kernels ------------------------------------------------
  * A block takes PARENTS consecutive parents at a time:
  *   A0  threads 0..PARENTS-1 count the moves of their parent; block exclusive scan
@@ -610,9 +684,10 @@ struct TileOut {
 /* In TILE_EXPAND / TILE_MOVES the per-parent counts come from the global scan (`prefix`, built by
  * k_count + k_scan_*), which also fixes where the tile's output starts; in TILE_LEAF they are
  * computed here and scanned within the block. */
-template <TileMode MODE, bool MULTI_ROOT, class CFG>
+template <TileMode MODE, Accounting ACC, class CFG>
 __global__ void __launch_bounds__(CFG::THREADS, CFG::MIN_BLOCKS)
 k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restrict__ prefix, TileOut out) {
+  constexpr bool MULTI_ROOT = ACC == PER_ROOT;
   constexpr int PARENTS = CFG::PARENTS, POOL = CFG::POOL, GROUPS = CFG::GROUPS, GT = CFG::GROUP_THREADS;
   constexpr int SYNC = GROUPS == 1 ? 0 : GT; /* 0: plain __syncthreads */
   constexpr bool LEAF = MODE == TILE_LEAF;
@@ -687,12 +762,13 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
           const u32 k = count_moves_white(q.white, q.pawns, q.knights, q.bishops, q.rooks, q.queens, q.kings,
                                           meta_castling(q.meta) & 3, meta_ep(q.meta), tb);
           if (MULTI_ROOT) atomicAdd(&sh.parent_nodes[parent], k);
-          else acc += k;
+          else acc += ACC == WEIGHTED ? k * in.mult[first + tile * PARENTS + parent] : (u64)k;
         } else {
           make_move(q, tb, (u16)(e & 0xFFFF));
           const size_t o = (size_t)(out_base + w + c);
           store_pos(out.children.rec, out.children.stride, o, q);
           if (MULTI_ROOT) out.children.roots[o] = in.roots[first + tile * PARENTS + parent];
+          if (ACC == WEIGHTED) out.children.mult[o] = in.mult[first + tile * PARENTS + parent];
         }
       }
       group_sync<SYNC>(group);

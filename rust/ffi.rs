@@ -35,6 +35,7 @@ pub struct Timing {
     pub leaf_kernel_launches: u64,
     pub leaf_parents: u64,
     pub leaf_children: u64,
+    pub merged_records: u64,
 }
 
 #[repr(C)]
@@ -61,6 +62,7 @@ extern "C" {
     pub fn pabi_cuda_device(ctx: *const Ctx) -> i32;
 
     pub fn pabi_cuda_perft(ctx: *mut Ctx, root: *const RawPosition, depth: u8, nodes: *mut u64, t: *mut Timing) -> i32;
+    pub fn pabi_cuda_perft_hashed(ctx: *mut Ctx, root: *const RawPosition, depth: u8, nodes: *mut u64, t: *mut Timing) -> i32;
     pub fn pabi_cuda_perft_batch(ctx: *mut Ctx, roots: *const RawPosition, n: usize, depth: u8, nodes_out: *mut u64,
                                  t: *mut Timing) -> i32;
     pub fn pabi_cuda_perft_shard(ctx: *mut Ctx, root: *const RawPosition, depth: u8, split_ply: u32, shard_index: u32,

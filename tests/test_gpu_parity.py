@@ -85,6 +85,18 @@ def test_perft_depth_0_1_2(pb, engine):
         assert [engine.perft(p, d) for d in range(4)] == [1, 0, 0, 0]
 
 
+def test_hashed_perft_is_exact(pb, engine, small_engine, vectors):
+    """Transposition merging changes the work, never the count: every reference vector, also with chunked frontiers."""
+    for case in vectors["perft"] + vectors["bench_perft"]:
+        assert engine.perft_hashed(fen_pos(pb, case["fen"]), case["depth"]) == case["nodes"], case
+        if case["nodes"] < 200_000_000:
+            assert small_engine.perft_hashed(fen_pos(pb, case["fen"]), case["depth"]) == case["nodes"], case
+    assert engine.perft_hashed(pb.Position.starting(), 8) == 84_998_978_956
+    assert engine.last_timing.merged_records > 0
+    for d in range(4):
+        assert engine.perft_hashed(pb.Position.from_fen(KIWIPETE), d) == [1, 48, 2039, 97862][d]
+
+
 def test_chunked_search_gives_the_same_counts(pb, small_engine, vectors):
     for case in vectors["perft"]:
         if 100_000 < case["nodes"] < 200_000_000:

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     L = _native.lib()
     for name in declared:
         assert getattr(L, name) is not None
-    assert C.sizeof(_native.PositionStruct) == 112 and C.sizeof(_native.Timing) == 72
+    assert C.sizeof(_native.PositionStruct) == 112 and C.sizeof(_native.Timing) == 80
 
 
 def test_no_cpu_fallback_without_a_device():
