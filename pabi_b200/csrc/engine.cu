@@ -47,6 +47,17 @@ struct Buffer {
   size_t bytes = 0;
 };
 
+/* growable device scratch of a context; a call may use each slot for one thing */
+enum Scratch {
+  S_STAGING = 0, /* host positions (AoS) on their way in */
+  S_SMALL_A,     /* offsets / seeds / flags / moves-in */
+  S_SMALL_B,     /* moves-out / counts / records */
+  S_AOS_OUT,     /* positions (AoS) on their way out */
+  S_COUNTS,      /* u32 per record: move counts of the device-resident API, slots of the merge table */
+  S_PREFIX,      /* u64 per record: scan of the device-resident API */
+  S_SLOTS
+};
+
 } /* namespace */
 
 struct pabi_cuda_ctx {
@@ -73,7 +84,7 @@ struct pabi_cuda_ctx {
   u64* h_result = nullptr; /* pinned */
   unsigned long long* d_nodes = nullptr;
   size_t nodes_cap = 0;
-  Buffer scratch[6];
+  Buffer scratch[S_SLOTS];
   int tile_variant = 0;
   std::string error;
   /* per-call statistics */
@@ -260,7 +271,7 @@ size_t merge_transpositions(pabi_cuda_ctx* ctx, int lv, size_t n) {
     CK(cudaMalloc(&ctx->d_owner, table * sizeof(u32)));
     ctx->merge_table = table;
   }
-  u32* slot_of = (u32*)ensure(ctx, 4, n * sizeof(u32));
+  u32* slot_of = (u32*)ensure(ctx, S_COUNTS, n * sizeof(u32));
   alloc_level(ctx, ctx->merge_level, cur.cap);
   ensure_mult(ctx, ctx->merge_level);
   CK(cudaMemsetAsync(ctx->d_tags, 0, table * sizeof(unsigned long long), ctx->stream));
@@ -370,7 +381,7 @@ struct CallTimer {
 /* Upload n positions (host AoS) into level 0 as SoA with roots = index. */
 void upload_roots(pabi_cuda_ctx* ctx, const pabi_position_t* pos, size_t n) {
   alloc_level(ctx, ctx->levels[0], n > 4096 ? n : 4096);
-  void* staging = ensure(ctx, 0, n * sizeof(pabi_position_t));
+  void* staging = ensure(ctx, S_STAGING, n * sizeof(pabi_position_t));
   CK(cudaMemcpyAsync(staging, pos, n * sizeof(pabi_position_t), cudaMemcpyHostToDevice, ctx->stream));
   Level& l0 = ctx->levels[0];
   k_pack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>((const PositionImage*)staging, n, l0.rec, l0.cap, 0, l0.roots);
@@ -645,7 +656,7 @@ int pabi_cuda_in_check_batch(pabi_cuda_ctx* ctx, const pabi_position_t* position
     }
     upload_roots(ctx, positions, n);
     Level& l0 = ctx->levels[0];
-    u8* d_out = (u8*)ensure(ctx, 1, n);
+    u8* d_out = (u8*)ensure(ctx, S_SMALL_A, n);
     timer.begin_device();
     k_in_check<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, l0.rec, l0.cap, n, d_out);
     LAUNCHED();
@@ -670,7 +681,7 @@ int pabi_cuda_attack_info_batch(pabi_cuda_ctx* ctx, const pabi_position_t* posit
     }
     upload_roots(ctx, positions, n);
     Level& l0 = ctx->levels[0];
-    u64* d_out = (u64*)ensure(ctx, 1, 5 * n * sizeof(u64));
+    u64* d_out = (u64*)ensure(ctx, S_SMALL_A, 5 * n * sizeof(u64));
     timer.begin_device();
     k_attack_info<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, l0.rec, l0.cap, n, d_out);
     LAUNCHED();
@@ -698,9 +709,9 @@ int pabi_cuda_random_playouts(pabi_cuda_ctx* ctx, const pabi_position_t* starts,
     upload_roots(ctx, starts, n_games);
     Level& l0 = ctx->levels[0];
     const size_t slots = n_games * (size_t)per_game_cap;
-    u64* d_seeds = (u64*)ensure(ctx, 1, n_games * sizeof(u64));
-    u32* d_counts = (u32*)ensure(ctx, 2, n_games * sizeof(u32));
-    PositionImage* d_out = (PositionImage*)ensure(ctx, 3, slots * sizeof(PositionImage));
+    u64* d_seeds = (u64*)ensure(ctx, S_SMALL_A, n_games * sizeof(u64));
+    u32* d_counts = (u32*)ensure(ctx, S_SMALL_B, n_games * sizeof(u32));
+    PositionImage* d_out = (PositionImage*)ensure(ctx, S_AOS_OUT, slots * sizeof(PositionImage));
     CK(cudaMemcpyAsync(d_seeds, seeds, n_games * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
     timer.begin_device();
     k_random_playouts<<<grid_for(ctx, n_games, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(
@@ -766,7 +777,7 @@ int pabi_cuda_games_create(pabi_cuda_ctx* ctx, const pabi_position_t* roots, siz
     CK(cudaMalloc(&games->d_applied, n * sizeof(u32)));
     CK(cudaMalloc(&games->d_seeds, n * sizeof(u64)));
     CK(cudaMemsetAsync(gs.overflow, 0, sizeof(u32), ctx->stream));
-    void* staging = ensure(ctx, 0, n * sizeof(pabi_position_t));
+    void* staging = ensure(ctx, S_STAGING, n * sizeof(pabi_position_t));
     CK(cudaMemcpyAsync(staging, roots, n * sizeof(pabi_position_t), cudaMemcpyHostToDevice, ctx->stream));
     k_pack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>((const PositionImage*)staging, n, gs.rec, n, 0, nullptr);
     CK(cudaGetLastError());
@@ -796,8 +807,8 @@ int pabi_cuda_games_actions(pabi_cuda_games* games, uint32_t* offsets, pabi_move
   pabi_cuda_ctx* ctx = games->ctx;
   try {
     const size_t n = games->gs.n;
-    u32* d_offsets = (u32*)ensure(ctx, 1, (n + 1) * sizeof(u32));
-    u16* d_moves = moves_cap ? (u16*)ensure(ctx, 2, moves_cap * sizeof(u16)) : nullptr;
+    u32* d_offsets = (u32*)ensure(ctx, S_SMALL_A, (n + 1) * sizeof(u32));
+    u16* d_moves = moves_cap ? (u16*)ensure(ctx, S_SMALL_B, moves_cap * sizeof(u16)) : nullptr;
     uint64_t total = 0;
     const int rc = pabi_cuda_generate_moves_device(ctx, games->gs.rec, n, n, d_offsets, d_moves, moves_cap, &total, nullptr);
     if (rc != 0 && rc != -2) return rc;
@@ -847,7 +858,7 @@ int pabi_cuda_games_positions(pabi_cuda_games* games, pabi_position_t* out) {
   try {
     CK(cudaSetDevice(ctx->device));
     const size_t n = games->gs.n;
-    PositionImage* d_out = (PositionImage*)ensure(ctx, 3, n * sizeof(PositionImage));
+    PositionImage* d_out = (PositionImage*)ensure(ctx, S_AOS_OUT, n * sizeof(PositionImage));
     k_unpack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(games->gs.rec, n, n, d_out);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, d_out, n * sizeof(PositionImage), cudaMemcpyDeviceToHost, ctx->stream));
@@ -893,9 +904,9 @@ int pabi_cuda_make_moves_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positi
     }
     upload_roots(ctx, positions, n);
     Level& l0 = ctx->levels[0];
-    u16* d_moves = (u16*)ensure(ctx, 1, n * sizeof(u16));
-    u64* d_rec = (u64*)ensure(ctx, 2, n * POS_WORDS * sizeof(u64));
-    PositionImage* d_out = (PositionImage*)ensure(ctx, 3, n * sizeof(PositionImage));
+    u16* d_moves = (u16*)ensure(ctx, S_SMALL_A, n * sizeof(u16));
+    u64* d_rec = (u64*)ensure(ctx, S_SMALL_B, n * POS_WORDS * sizeof(u64));
+    PositionImage* d_out = (PositionImage*)ensure(ctx, S_AOS_OUT, n * sizeof(PositionImage));
     CK(cudaMemcpyAsync(d_moves, moves, n * sizeof(u16), cudaMemcpyHostToDevice, ctx->stream));
     timer.begin_device();
     k_make_moves<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, l0.rec, l0.cap, n, d_moves,
@@ -919,8 +930,8 @@ int pabi_cuda_generate_moves_device(pabi_cuda_ctx* ctx, const uint64_t* device_r
   try {
     CK(cudaSetDevice(ctx->device));
     CallTimer timer(ctx);
-    u32* counts = (u32*)ensure(ctx, 4, (n + 1) * sizeof(u32));
-    u64* prefix = (u64*)ensure(ctx, 5, (n + 2) * sizeof(u64));
+    u32* counts = (u32*)ensure(ctx, S_COUNTS, (n + 1) * sizeof(u32));
+    u64* prefix = (u64*)ensure(ctx, S_PREFIX, (n + 2) * sizeof(u64));
     timer.begin_device();
     if (n) {
       count_and_scan(ctx, device_records, stride, 0, n, counts, prefix);
@@ -952,7 +963,7 @@ int pabi_cuda_pack_records(pabi_cuda_ctx* ctx, const pabi_position_t* positions,
   try {
     CK(cudaSetDevice(ctx->device));
     if (n == 0) return 0;
-    void* staging = ensure(ctx, 0, n * sizeof(pabi_position_t));
+    void* staging = ensure(ctx, S_STAGING, n * sizeof(pabi_position_t));
     CK(cudaMemcpyAsync(staging, positions, n * sizeof(pabi_position_t), cudaMemcpyHostToDevice, ctx->stream));
     k_pack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>((const PositionImage*)staging, n, device_records, stride, 0, nullptr);
     CK(cudaGetLastError());
@@ -977,8 +988,8 @@ int pabi_cuda_generate_moves_batch(pabi_cuda_ctx* ctx, const pabi_position_t* po
     if (n >= 0xFFFFFFFFull / 256) return bad_arg(ctx, "batch too large for 32-bit CSR offsets");
     upload_roots(ctx, positions, n);
     Level& l0 = ctx->levels[0];
-    u32* d_offsets = (u32*)ensure(ctx, 1, (n + 1) * sizeof(u32));
-    u16* d_moves = moves_cap ? (u16*)ensure(ctx, 2, moves_cap * sizeof(u16)) : nullptr;
+    u32* d_offsets = (u32*)ensure(ctx, S_SMALL_A, (n + 1) * sizeof(u32));
+    u16* d_moves = moves_cap ? (u16*)ensure(ctx, S_SMALL_B, moves_cap * sizeof(u16)) : nullptr;
     alloc_level(ctx, l0, n); /* counts/prefix of level 0 are the sizing arrays */
     timer.begin_device();
     count_and_scan(ctx, l0.rec, l0.cap, 0, n, l0.counts, l0.prefix);
@@ -1020,7 +1031,7 @@ int pabi_cuda_expand_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions,
     if (n >= 0xFFFFFFFFull / 256) return bad_arg(ctx, "batch too large for 32-bit CSR offsets");
     upload_roots(ctx, positions, n);
     Level& l0 = ctx->levels[0];
-    u32* d_offsets = (u32*)ensure(ctx, 1, (n + 1) * sizeof(u32));
+    u32* d_offsets = (u32*)ensure(ctx, S_SMALL_A, (n + 1) * sizeof(u32));
     timer.begin_device();
     count_and_scan(ctx, l0.rec, l0.cap, 0, n, l0.counts, l0.prefix);
     k_prefix_to_offsets<<<grid_for(ctx, n + 1, 256, 8), 256, 0, ctx->stream>>>(l0.prefix, n, d_offsets);
@@ -1039,7 +1050,7 @@ int pabi_cuda_expand_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions,
       Level& l1 = ctx->levels[1];
       alloc_level(ctx, l1, ctx->capacity);
       launch_expand(ctx, PER_ROOT, frontier_of(l0), 0, n, l0.prefix, frontier_of(l1));
-      PositionImage* d_out = (PositionImage*)ensure(ctx, 3, total * sizeof(PositionImage));
+      PositionImage* d_out = (PositionImage*)ensure(ctx, S_AOS_OUT, total * sizeof(PositionImage));
       k_unpack<<<grid_for(ctx, total, 256, 8), 256, 0, ctx->stream>>>(l1.rec, l1.cap, total, d_out);
       LAUNCHED();
       timer.end_device();
