@@ -158,6 +158,18 @@ int pabi_cuda_random_playouts(pabi_cuda_ctx* ctx, const pabi_position_t* starts,
                               uint32_t max_plies, uint32_t stride, uint32_t per_game_cap, pabi_position_t* out,
                               uint32_t* counts, pabi_timing_t* timing);
 
+/* FEN / EPD book parsing on the device (impl TryFrom<&str> for Position, src/chess/position.rs:809-821, i.e.
+ * trim + optional "fen "/"epd " prefix + from_fen :157-275 + validate :934-1032), one thread per line:
+ * line i is text[line_offsets[i] .. line_offsets[i+1]) (a trailing '\n' is ignored).  status[i] = 0 and
+ * out[i] = the position, or a negative class (-1 placement, -2 side to move, -3 castling, -4 en passant,
+ * -5 halfmove clock, -6 fullmove counter, -7 trailing fields, -8 illegal position) and out[i] zeroed;
+ * pabi_position_parse on the host gives the reference's message for a rejected line. */
+int pabi_cuda_parse_batch(pabi_cuda_ctx* ctx, const char* text, const uint64_t* line_offsets /* [n+1] */, size_t n,
+                          pabi_position_t* out /* [n] */, int8_t* status /* [n] */, pabi_timing_t* timing);
+/* The 64-byte device record of a position as a wire / on-disk format */
+void pabi_position_pack64(const pabi_position_t* p, uint64_t out[8]);
+void pabi_position_unpack64(const uint64_t in[8], pabi_position_t* out);
+
 /* ---- Game environment: `Game` (src/chess/game.rs:21-111) for a batch of games ------------------
  * State lives on the device: position, perspective (the root's side to move, game.rs:36), the
  * repetition table (src/chess/zobrist.rs:10-36) and the threefold flag.  The Syzygy adjudication

@@ -80,6 +80,7 @@ EXPORTS = (
     "pabi_cuda_generate_moves_batch", "pabi_cuda_count_moves_batch", "pabi_cuda_in_check_batch",
     "pabi_cuda_attack_info_batch", "pabi_cuda_make_moves_batch", "pabi_cuda_expand_batch", "pabi_cuda_pack_records",
     "pabi_cuda_generate_moves_device", "pabi_cuda_random_playouts",
+    "pabi_cuda_parse_batch", "pabi_position_pack64", "pabi_position_unpack64",
     "pabi_cuda_games_create", "pabi_cuda_games_destroy", "pabi_cuda_games_actions", "pabi_cuda_games_apply",
     "pabi_cuda_games_result", "pabi_cuda_games_positions", "pabi_cuda_games_play_random",
 )
@@ -130,6 +131,11 @@ def lib() -> C.CDLL:
     L.pabi_cuda_make_moves_batch.argtypes = [vp, vp, vp, sz, vp, T]
     L.pabi_cuda_expand_batch.argtypes = [vp, vp, sz, vp, vp, sz, T]
     L.pabi_cuda_random_playouts.argtypes = [vp, vp, vp, sz, u32, u32, u32, vp, vp, T]
+    L.pabi_cuda_parse_batch.argtypes = [vp, C.c_char_p, vp, sz, vp, vp, T]
+    L.pabi_position_pack64.argtypes = [P, C.POINTER(C.c_uint64)]
+    L.pabi_position_pack64.restype = None
+    L.pabi_position_unpack64.argtypes = [C.POINTER(C.c_uint64), P]
+    L.pabi_position_unpack64.restype = None
     L.pabi_cuda_games_create.argtypes = [vp, vp, sz, u32, C.POINTER(vp)]
     L.pabi_cuda_games_destroy.argtypes = [vp]
     L.pabi_cuda_games_destroy.restype = None

@@ -221,6 +221,20 @@ class Engine:
         self.last_timing = t
         return [out[g * cap: g * cap + int(counts[g])] for g in range(len(arr))]
 
+    def parse_batch(self, lines: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
+        """FEN / EPD lines parsed on the device (`pabi_cuda_parse_batch`, `Position::try_from` semantics):
+        (positions, status) with status 0 = accepted, < 0 = the rejection class."""
+        encoded = [l.encode("utf-8") for l in lines]
+        offsets = np.zeros(len(encoded) + 1, dtype=np.uint64)
+        np.cumsum([len(b) for b in encoded], out=offsets[1:])
+        text = b"".join(encoded)
+        out = np.empty(len(encoded), dtype=POSITION_DTYPE)
+        status, t = np.zeros(len(encoded), dtype=np.int8), Timing()
+        self._check(_native.lib().pabi_cuda_parse_batch(self._ctx, text, offsets.ctypes.data, len(encoded), out.ctypes.data,
+                                                        status.ctypes.data, C.byref(t)))
+        self.last_timing = t
+        return out, status
+
     def expand_batch(self, positions) -> Tuple[np.ndarray, np.ndarray]:
         """Every child of every position in generate_moves order: (offsets[n+1], children)."""
         arr = _as_array(positions)
@@ -291,6 +305,19 @@ class Position:
     @classmethod
     def from_record(cls, record) -> "Position":
         return cls(PositionStruct.from_buffer_copy(np.asarray(record).tobytes()))
+
+    def pack64(self) -> np.ndarray:
+        """The 64-byte record of the position (`pabi_position_pack64`): the device / wire format."""
+        out = np.zeros(8, dtype=np.uint64)
+        _native.lib().pabi_position_pack64(C.byref(self.raw), out.ctypes.data_as(C.POINTER(C.c_uint64)))
+        return out
+
+    @classmethod
+    def unpack64(cls, words) -> "Position":
+        w = np.ascontiguousarray(np.asarray(words, dtype=np.uint64))
+        p = cls()
+        _native.lib().pabi_position_unpack64(w.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(p.raw))
+        return p
 
     def clone(self) -> "Position":
         q = Position()

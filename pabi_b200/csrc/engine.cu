@@ -518,6 +518,7 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     CK(cudaFuncSetAttribute(k_attack_info, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_make_moves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_random_playouts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_parse_fens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_games_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_games_result, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_games_play_random, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
@@ -889,6 +890,42 @@ int pabi_cuda_games_play_random(pabi_cuda_games* games, const uint64_t* seeds, u
     return games_overflowed(games);
   } catch (const CudaFail& f) {
     return fail(ctx, f);
+  }
+}
+
+int pabi_cuda_parse_batch(pabi_cuda_ctx* ctx, const char* text, const uint64_t* line_offsets, size_t n, pabi_position_t* out,
+                          int8_t* status, pabi_timing_t* timing) {
+  if (!ctx || (n && (!text || !line_offsets || !out || !status))) return bad_arg(ctx, "null argument");
+  try {
+    CK(cudaSetDevice(ctx->device));
+    CallTimer timer(ctx);
+    if (n == 0) {
+      timer.begin_device(), timer.end_device(), timer.finish(timing, 0);
+      return 0;
+    }
+    const size_t bytes = (size_t)(line_offsets[n] - line_offsets[0]);
+    char* d_text = (char*)ensure(ctx, S_STAGING, bytes + 16);
+    u64* d_offsets = (u64*)ensure(ctx, S_PREFIX, (n + 1) * sizeof(u64));
+    signed char* d_status = (signed char*)ensure(ctx, S_SMALL_A, n);
+    PositionImage* d_out = (PositionImage*)ensure(ctx, S_AOS_OUT, n * sizeof(PositionImage));
+    std::vector<u64> rel(n + 1);
+    for (size_t i = 0; i <= n; i++) rel[i] = line_offsets[i] - line_offsets[0];
+    CK(cudaMemcpyAsync(d_text, text + line_offsets[0], bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_offsets, rel.data(), (n + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    timer.begin_device();
+    k_parse_fens<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, d_text, d_offsets, n, d_out,
+                                                                                            d_status);
+    LAUNCHED();
+    timer.end_device();
+    CK(cudaMemcpyAsync(out, d_out, n * sizeof(PositionImage), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, ctx->stream));
+    timer.finish(timing, bytes + 112 * n);
+    return 0;
+  } catch (const CudaFail& f) {
+    return fail(ctx, f);
+  } catch (const std::bad_alloc&) {
+    ctx->error = "out of host memory";
+    return -3;
   }
 }
 

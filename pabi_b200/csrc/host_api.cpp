@@ -294,6 +294,19 @@ int pabi_position_to_fen(const pabi_position_t* p, char* out, size_t cap) {
   return (int)s.size();
 }
 
+void pabi_position_pack64(const pabi_position_t* p, uint64_t out[8]) {
+  const Pos r = pack_record(*p);
+  out[0] = r.white, out[1] = r.pawns, out[2] = r.knights, out[3] = r.bishops;
+  out[4] = r.rooks, out[5] = r.queens, out[6] = r.kings, out[7] = r.meta;
+}
+
+void pabi_position_unpack64(const uint64_t in[8], pabi_position_t* out) {
+  Pos r;
+  r.white = in[0], r.pawns = in[1], r.knights = in[2], r.bishops = in[3];
+  r.rooks = in[4], r.queens = in[5], r.kings = in[6], r.meta = in[7];
+  *out = unpack_record(r, 0);
+}
+
 int pabi_move_from_uci(const char* uci, pabi_move_t* out) {
   if (!uci || !out) return -1;
   const size_t n = std::strlen(uci);

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include "chess.cuh"
+#include "fen.cuh"
 
 namespace pabi {
 
@@ -328,6 +329,30 @@ k_random_playouts(DeviceTables dt, const u64* __restrict__ rec, size_t stride_re
       make_move(p, tb, chosen);
     }
     counts[g] = written;
+  }
+}
+
+/* FEN / EPD lines -> positions, one thread per line (fen.cuh); line i is text[offsets[i] .. offsets[i+1]) */
+__global__ void __launch_bounds__(FLAT_THREADS)
+k_parse_fens(DeviceTables dt, const char* __restrict__ text, const u64* __restrict__ offsets, size_t n, PositionImage* __restrict__ out,
+             signed char* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SharedTables* st = reinterpret_cast<SharedTables*>(smem);
+  stage_tables(st, dt.image);
+  const Tables tb{st, dt.g};
+  for (size_t i = (size_t)blockIdx.x * FLAT_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * FLAT_THREADS) {
+    ParsedPosition p;
+    size_t len = (size_t)(offsets[i + 1] - offsets[i]);
+    const char* line = text + offsets[i];
+    if (len && line[len - 1] == '\n') --len; /* a line may carry its terminator */
+    const int rc = parse_position(line, len, tb, p);
+    status[i] = (signed char)rc;
+    PositionImage q;
+    for (int k = 0; k < 6; k++) q.white[k] = rc == 0 ? p.white[k] : 0, q.black[k] = rc == 0 ? p.black[k] : 0;
+    q.hash = 0;
+    q.fullmove = rc == 0 ? p.fullmove : 0, q.castling = rc == 0 ? p.castling : 0, q.stm = rc == 0 ? p.stm : 0;
+    q.halfmove = rc == 0 ? p.halfmove : 0, q.ep = rc == 0 ? p.ep : 0, q.pad[0] = q.pad[1] = 0;
+    out[i] = q;
   }
 }
 

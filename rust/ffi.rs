@@ -84,6 +84,10 @@ extern "C" {
                                   children: *mut RawPosition, children_cap: usize, t: *mut Timing) -> i32;
     pub fn pabi_cuda_random_playouts(ctx: *mut Ctx, starts: *const RawPosition, seeds: *const u64, n_games: usize, max_plies: u32,
                                      stride: u32, per_game_cap: u32, out: *mut RawPosition, counts: *mut u32, t: *mut Timing) -> i32;
+    pub fn pabi_cuda_parse_batch(ctx: *mut Ctx, text: *const c_char, line_offsets: *const u64, n: usize, out: *mut RawPosition,
+                                 status: *mut i8, t: *mut Timing) -> i32;
+    pub fn pabi_position_pack64(p: *const RawPosition, out: *mut u64);
+    pub fn pabi_position_unpack64(words: *const u64, out: *mut RawPosition);
     // Game environment (src/chess/game.rs:21-111 without the Syzygy branch); `Games` is an opaque handle like `Ctx`
     pub fn pabi_cuda_games_create(ctx: *mut Ctx, roots: *const RawPosition, n: usize, history_cap: u32, out: *mut *mut Games) -> i32;
     pub fn pabi_cuda_games_destroy(games: *mut Games);

@@ -5,6 +5,7 @@
  * exact logic the kernels inline with the oracle on millions of positions
  * without a GPU.  Never linked into libpabi_b200.so.
  */
+#include "../../pabi_b200/csrc/fen.cuh"
 #include "../../pabi_b200/csrc/record.h"
 #include "../../pabi_b200/csrc/tables.h"
 
@@ -49,6 +50,19 @@ void hostcheck_analysis(const pabi_position_t* p, uint64_t out[5]) {
 void hostcheck_attack_info(const pabi_position_t* p, uint64_t out[5]) {
   const AttackInfoOut a = attack_info(pack_record(*p), host_tb());
   out[0] = a.attacks, out[1] = a.checkers, out[2] = a.pins, out[3] = a.xrays, out[4] = a.safe_king_squares;
+}
+
+/* the device FEN parser (fen.cuh) on the host */
+int hostcheck_parse(const char* text, size_t len, pabi_position_t* out) {
+  ParsedPosition p;
+  const int rc = parse_position(text, len, host_tb(), p);
+  __builtin_memset(out, 0, sizeof *out);
+  if (rc == 0) {
+    for (int k = 0; k < 6; k++) out->white[k] = p.white[k], out->black[k] = p.black[k];
+    out->fullmove_counter = p.fullmove, out->castling = p.castling, out->side_to_move = p.stm;
+    out->halfmove_clock = p.halfmove, out->en_passant_square = p.ep;
+  }
+  return rc;
 }
 
 static uint64_t perft_rec(const Pos& p, const Tables& tb, int depth) {

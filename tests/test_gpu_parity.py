@@ -249,6 +249,33 @@ def test_random_playouts_on_device_equal_the_oracle_driver(pb, engine):
         assert total >= 600
 
 
+def test_books_parsed_on_the_device(pb, engine, vectors, playout_positions):
+    """pabi_cuda_parse_batch: every line gets the host parser's verdict and, when accepted, its position."""
+    import random
+    from test_host_api import REJECTED
+    rng = random.Random(5)
+    lines = list(vectors["fen"]["roundtrip"]) + list(vectors["fen"]["try_from_ok"]) + list(vectors["fen"]["try_from_err"])
+    lines += REJECTED + [c["fen"] for c in vectors["fen"]["errors"]]
+    for i in range(0, 20000, 7):
+        fen = oracle.to_fen(oracle.Position.from_buffer_copy(playout_positions[i].tobytes()))
+        lines.append(fen if i % 3 else "epd " + " ".join(fen.split()[:4]) + "\n")
+        chars = list(fen)
+        chars[rng.randrange(len(chars))] = rng.choice("pnbrqkPNBRQK12345678/ wb-KQkqabcdefgh0")
+        lines.append("".join(chars))
+    positions, status = engine.parse_batch(lines)
+    accepted = 0
+    for i, line in enumerate(lines):
+        try:
+            want = pb.Position.try_from(line)
+        except ValueError:
+            assert status[i] < 0, line
+            continue
+        assert status[i] == 0, line
+        assert positions[i].tobytes() == bytes(want.raw), line
+        accepted += 1
+    assert 3000 < accepted < len(lines)
+
+
 # ---- Game environment (src/chess/game.rs:21-111 without the Syzygy branch) ----
 
 def test_reference_game_tests(pb, engine):

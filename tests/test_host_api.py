@@ -26,7 +26,7 @@ def sanitize_fen(text: str) -> str:
 
 def test_library_exports_every_declared_symbol():
     header = (ROOT / "include" / "pabi_cuda.h").read_text()
-    declared = set(re.findall(r"\b(pabi_(?:cuda|position|move)_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(pabi_(?:cuda|position|move)_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_native.EXPORTS)
     L = _native.lib()
     for name in declared:
@@ -145,3 +145,16 @@ def test_move_text():
     for bad in ("", "e2", "e2e9", "e2e4x", "e2e4qq", "i2e4"):
         with pytest.raises(ValueError):
             pb.Move.from_uci(bad)
+
+
+def test_pack64_round_trip():
+    """The 64-byte record as a wire format: pack / unpack reproduces the position (hash is not carried)."""
+    for g in range(10):
+        arr = oracle.random_playout(oracle.starting(), 0x64640000 + g, 120, 5)
+        for i in range(len(arr)):
+            o = oracle.Position.from_buffer_copy(arr[i].tobytes())
+            p = pb.Position.from_fen(oracle.to_fen(o))
+            words = p.pack64()
+            assert len(words) == 8
+            q = pb.Position.unpack64(words)
+            assert bytes(q.raw) == bytes(p.raw)
