@@ -228,6 +228,26 @@ struct PositionImage { /* == pabi_position_t */
 };
 static_assert(sizeof(PositionImage) == 112, "pabi_position_t image");
 
+__device__ __forceinline__ PositionImage image_of(const Pos& p) {
+  PositionImage q;
+  const u64 w = p.white;
+  q.white[0] = p.kings & w, q.black[0] = p.kings & ~w;
+  q.white[1] = p.queens & w, q.black[1] = p.queens & ~w;
+  q.white[2] = p.rooks & w, q.black[2] = p.rooks & ~w;
+  q.white[3] = p.bishops & w, q.black[3] = p.bishops & ~w;
+  q.white[4] = p.knights & w, q.black[4] = p.knights & ~w;
+  q.white[5] = p.pawns & w, q.black[5] = p.pawns & ~w;
+  q.hash = 0;
+  q.fullmove = (u16)meta_fullmove(p.meta);
+  q.castling = (u8)meta_castling(p.meta);
+  q.stm = (u8)meta_stm(p.meta);
+  q.halfmove = (u8)meta_halfmove(p.meta);
+  q.ep = (u8)meta_ep(p.meta);
+  q.pad[0] = q.pad[1] = 0;
+  return q;
+}
+
+
 __global__ void k_pack(const PositionImage* __restrict__ in, size_t n, u64* __restrict__ rec, size_t stride, size_t first,
                        u32* __restrict__ roots) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -247,44 +267,8 @@ __global__ void k_pack(const PositionImage* __restrict__ in, size_t n, u64* __re
 }
 
 __global__ void k_unpack(const u64* __restrict__ rec, size_t stride, size_t n, PositionImage* __restrict__ out) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const Pos p = load_pos(rec, stride, i);
-    PositionImage q;
-    const u64 w = p.white;
-    q.white[0] = p.kings & w, q.black[0] = p.kings & ~w;
-    q.white[1] = p.queens & w, q.black[1] = p.queens & ~w;
-    q.white[2] = p.rooks & w, q.black[2] = p.rooks & ~w;
-    q.white[3] = p.bishops & w, q.black[3] = p.bishops & ~w;
-    q.white[4] = p.knights & w, q.black[4] = p.knights & ~w;
-    q.white[5] = p.pawns & w, q.black[5] = p.pawns & ~w;
-    q.hash = 0;
-    q.fullmove = (u16)meta_fullmove(p.meta);
-    q.castling = (u8)meta_castling(p.meta);
-    q.stm = (u8)meta_stm(p.meta);
-    q.halfmove = (u8)meta_halfmove(p.meta);
-    q.ep = (u8)meta_ep(p.meta);
-    q.pad[0] = q.pad[1] = 0;
-    out[i] = q;
-  }
-}
-
-__device__ __forceinline__ PositionImage image_of(const Pos& p) {
-  PositionImage q;
-  const u64 w = p.white;
-  q.white[0] = p.kings & w, q.black[0] = p.kings & ~w;
-  q.white[1] = p.queens & w, q.black[1] = p.queens & ~w;
-  q.white[2] = p.rooks & w, q.black[2] = p.rooks & ~w;
-  q.white[3] = p.bishops & w, q.black[3] = p.bishops & ~w;
-  q.white[4] = p.knights & w, q.black[4] = p.knights & ~w;
-  q.white[5] = p.pawns & w, q.black[5] = p.pawns & ~w;
-  q.hash = 0;
-  q.fullmove = (u16)meta_fullmove(p.meta);
-  q.castling = (u8)meta_castling(p.meta);
-  q.stm = (u8)meta_stm(p.meta);
-  q.halfmove = (u8)meta_halfmove(p.meta);
-  q.ep = (u8)meta_ep(p.meta);
-  q.pad[0] = q.pad[1] = 0;
-  return q;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = image_of(load_pos(rec, stride, i));
 }
 
 __device__ __forceinline__ u64 splitmix64(u64& s) {
