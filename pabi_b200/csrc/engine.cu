@@ -247,8 +247,14 @@ void launch_expand(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t first
 
 /* K3: ordered move lists of records [0, n) at the offsets of `prefix`; the caller has checked the capacity */
 void launch_moves(pabi_cuda_ctx* ctx, const u64* rec, size_t stride, size_t n, const u64* prefix, u16* moves, u32* offsets) {
-  const TileOut out{Frontier{nullptr, nullptr, 0, nullptr}, moves, offsets, nullptr, nullptr};
-  launch_tile_cfg<TILE_MOVES, SINGLE_ROOT, TileDefault>(ctx, Frontier{const_cast<u64*>(rec), nullptr, stride, nullptr}, 0, n, prefix, out);
+  if (ctx->tile_variant == 9) { /* the block-level tile pipeline, kept for comparison (PABI_TILE_VARIANT=9) */
+    const TileOut out{Frontier{nullptr, nullptr, 0, nullptr}, moves, offsets, nullptr, nullptr};
+    launch_tile_cfg<TILE_MOVES, SINGLE_ROOT, TileDefault>(ctx, Frontier{const_cast<u64*>(rec), nullptr, stride, nullptr}, 0, n, prefix, out);
+    return;
+  }
+  k_moves_warp<<<grid_for(ctx, n, MOVES_THREADS, 1), MOVES_THREADS, sizeof(MovesShared), ctx->stream>>>(ctx->dt, rec, stride, n, prefix,
+                                                                                                      moves, offsets);
+  LAUNCHED();
 }
 
 /* Walks `remaining` plies below the n records of level `lv`, adding leaf counts
@@ -518,13 +524,14 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     CK(cudaFuncSetAttribute(k_attack_info, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_make_moves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_random_playouts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_moves_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MovesShared)));
     CK(cudaFuncSetAttribute(k_parse_fens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_games_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_games_result, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_games_play_random, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     if (const char* v = std::getenv("PABI_TILE_VARIANT")) {
       ctx->tile_variant = std::atoi(v);
-      if (ctx->tile_variant < 0 || ctx->tile_variant >= TILE_VARIANTS) ctx->tile_variant = 0;
+      if (ctx->tile_variant != 9 && (ctx->tile_variant < 0 || ctx->tile_variant >= TILE_VARIANTS)) ctx->tile_variant = 0;
     }
   } catch (const CudaFail& f) {
     std::fprintf(stderr, "pabi_cuda_create: %s\n", ctx->error.c_str());

@@ -564,6 +564,63 @@ __global__ void k_chunk_end(const u64* __restrict__ prefix, size_t start, size_t
   result[1] = prefix[lo] - base;
 }
 
+/* ---- K3: ordered move lists, warp-synchronous ------------------------------------------------
+ * Every warp owns 32 consecutive positions and a private pool in shared memory: each lane
+ * generates its position's moves (reference order) into the pool at the offset the global scan
+ * assigned, then the warp copies the pool to the CSR array with coalesced 64-byte stores.  No
+ * block-wide barrier: move generation times differ a lot between unrelated positions, and with the
+ * block-level tile pipeline 43 % of the stall samples were threads waiting for the slowest
+ * generator of their group (ncu, round 1). */
+constexpr int MOVES_THREADS = 1024;
+constexpr int MOVES_POOL = 2048; /* u16 entries per warp; an average warp needs ~900, the worst case 32 * 218 */
+
+struct MovesShared {
+  SharedTables tables;
+  u16 pool[MOVES_THREADS / 32][MOVES_POOL];
+};
+
+__global__ void __launch_bounds__(MOVES_THREADS, 1)
+k_moves_warp(DeviceTables dt, const u64* __restrict__ rec, size_t stride, size_t n, const u64* __restrict__ prefix,
+             u16* __restrict__ moves, u32* __restrict__ offsets) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  MovesShared& sh = *reinterpret_cast<MovesShared*>(smem);
+  stage_tables(&sh.tables, dt.image);
+  const Tables tb{&sh.tables, dt.g};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u16* pool = sh.pool[warp];
+  const size_t n_warps = (n + 31) / 32;
+  for (size_t wi = (size_t)blockIdx.x * (MOVES_THREADS / 32) + warp; wi < n_warps; wi += (size_t)gridDim.x * (MOVES_THREADS / 32)) {
+    const size_t first = wi * 32, i = first + lane;
+    const bool valid = i < n;
+    const u64 warp_prefix = prefix[first];
+    const u32 total = (u32)(prefix[min(first + 32, n)] - warp_prefix);
+    u32 off = 0, cnt = 0;
+    Pos p;
+    if (valid) {
+      const u64 mine = prefix[i];
+      off = (u32)(mine - warp_prefix);
+      cnt = (u32)(prefix[i + 1] - mine);
+      offsets[i] = (u32)(mine - prefix[0]);
+      if (i + 1 == n) offsets[n] = (u32)(prefix[n] - prefix[0]);
+      p = load_pos(rec, stride, i);
+    }
+    const u64 out_base = warp_prefix - prefix[0];
+    for (u32 w = 0; w < total; w += MOVES_POOL) {
+      if (cnt && off < w + MOVES_POOL && off + cnt > w) {
+        u32 j = off;
+        generate_moves(p, tb, [&](int from, int to, int promo, int) {
+          const u32 slot = j++ - w; /* wraps to a huge value below the window */
+          if (slot < (u32)MOVES_POOL) pool[slot] = pack_move(from, to, promo);
+        });
+      }
+      __syncwarp();
+      const u32 end = min(total - w, (u32)MOVES_POOL);
+      for (u32 c = lane; c < end; c += 32) moves[out_base + w + c] = pool[c];
+      __syncwarp();
+    }
+  }
+}
+
 /* ---- transposition merging (perft "with hashing", made exact) -------------------------------
  * Records of one ply that are the same position (placement, side to move, castling rights, en
  * passant square; the clocks do not influence perft) are merged into one record whose multiplicity
