@@ -217,7 +217,8 @@ void launch_leaf(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n) {
     ctx->leaf_events.push_back(e);
   }
   CK(cudaEventRecord(ctx->leaf_events[2 * ctx->leaf_launches], ctx->stream));
-  const TileOut out{Frontier{nullptr, nullptr, 0, nullptr}, nullptr, nullptr, ctx->d_nodes, ctx->d_visited};
+  CK(cudaMemsetAsync(ctx->d_visited + 1, 0, sizeof(unsigned long long), ctx->stream)); /* the tile ticket counter */
+  const TileOut out{Frontier{nullptr, nullptr, 0, nullptr}, nullptr, nullptr, ctx->d_nodes, ctx->d_visited, ctx->d_visited + 1};
   if (acc == PER_ROOT) {
     launch_tile_cfg<TILE_LEAF, PER_ROOT, TileDefault>(ctx, in, 0, n, nullptr, out);
   } else if (acc == WEIGHTED) {
@@ -239,7 +240,7 @@ void launch_leaf(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n) {
 
 /* K1: children of records [first, first + n) of `in`, at the offsets of `prefix` (count_and_scan) */
 void launch_expand(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t first, size_t n, const u64* prefix, Frontier children) {
-  const TileOut out{children, nullptr, nullptr, nullptr, nullptr};
+  const TileOut out{children, nullptr, nullptr, nullptr, nullptr, nullptr};
   if (acc == PER_ROOT) launch_tile_cfg<TILE_EXPAND, PER_ROOT, TileDefault>(ctx, in, first, n, prefix, out);
   else if (acc == WEIGHTED) launch_tile_cfg<TILE_EXPAND, WEIGHTED, TileDefault>(ctx, in, first, n, prefix, out);
   else launch_tile_cfg<TILE_EXPAND, SINGLE_ROOT, TileDefault>(ctx, in, first, n, prefix, out);
@@ -248,7 +249,7 @@ void launch_expand(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t first
 /* K3: ordered move lists of records [0, n) at the offsets of `prefix`; the caller has checked the capacity */
 void launch_moves(pabi_cuda_ctx* ctx, const u64* rec, size_t stride, size_t n, const u64* prefix, u16* moves, u32* offsets) {
   if (ctx->tile_variant == 9) { /* the block-level tile pipeline, kept for comparison (PABI_TILE_VARIANT=9) */
-    const TileOut out{Frontier{nullptr, nullptr, 0, nullptr}, moves, offsets, nullptr, nullptr};
+    const TileOut out{Frontier{nullptr, nullptr, 0, nullptr}, moves, offsets, nullptr, nullptr, nullptr};
     launch_tile_cfg<TILE_MOVES, SINGLE_ROOT, TileDefault>(ctx, Frontier{const_cast<u64*>(rec), nullptr, stride, nullptr}, 0, n, prefix, out);
     return;
   }
@@ -513,7 +514,7 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     ctx->dt.g.rook_attacks = ctx->d_rook;
     ctx->dt.g.rays = ctx->d_rays;
     CK(cudaMalloc(&ctx->d_result, 4 * sizeof(u64)));
-    CK(cudaMalloc(&ctx->d_visited, sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->d_visited, 2 * sizeof(unsigned long long))); /* [0] statistics, [1] tile tickets */
     CK(cudaMallocHost(&ctx->h_result, 4 * sizeof(u64)));
     /* kernels that stage the table image need more than the default 48 KB of dynamic shared memory */
     CK(cudaFuncSetAttribute(k_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));

@@ -716,6 +716,7 @@ struct TileGroupShared {
   u32 pool[CFG::POOL];
   u32 parent_nodes[CFG::PARENTS]; /* K2, multi-root: nodes below each parent */
   u32 warp_sums[CFG::GROUP_THREADS / 32 + 1];
+  unsigned long long next_tile; /* TILE_LEAF: the tile this group took from the ticket counter */
 };
 
 template <class CFG>
@@ -745,6 +746,7 @@ struct TileOut {
   u32* offsets;                     /* TILE_MOVES: offsets[i] = prefix[first + i] - prefix[first] (n + 1 entries) */
   unsigned long long* nodes;        /* TILE_LEAF: per-root (or single) leaf counts */
   unsigned long long* visited;      /* TILE_LEAF statistics: children generated */
+  unsigned long long* ticket;       /* TILE_LEAF: tiles are handed out dynamically (zeroed before the launch) */
 };
 
 /* In TILE_EXPAND / TILE_MOVES the per-parent counts come from the global scan (`prefix`, built by
@@ -767,7 +769,15 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
   u64 acc = 0;
   const size_t n_tiles = (n + PARENTS - 1) / PARENTS;
 
-  for (size_t tile = (size_t)blockIdx.x * GROUPS + group; tile < n_tiles; tile += (size_t)gridDim.x * GROUPS) {
+  /* K2 takes tiles from a ticket counter (their cost varies, and a static split leaves a tail of idle
+   * groups at the end of the launch); K1/K3 tiles are cheap and uniform enough for a static stride */
+  for (size_t tile = (size_t)blockIdx.x * GROUPS + group;; tile += (size_t)gridDim.x * GROUPS) {
+    if (LEAF) {
+      if (tid == 0) sh.next_tile = atomicAdd(out.ticket, 1ULL);
+      group_sync<SYNC>(group); /* the scan below separates this read from the next iteration's write */
+      tile = (size_t)sh.next_tile;
+    }
+    if (tile >= n_tiles) break;
     const size_t i = tile * PARENTS + tid;
     const bool valid = tid < PARENTS && i < n;
     u32 cnt = 0, off = 0, total;
