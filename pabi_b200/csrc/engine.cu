@@ -219,7 +219,10 @@ void launch_leaf(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n) {
   CK(cudaEventRecord(ctx->leaf_events[2 * ctx->leaf_launches], ctx->stream));
   CK(cudaMemsetAsync(ctx->d_visited + 1, 0, sizeof(unsigned long long), ctx->stream)); /* the tile ticket counter */
   const TileOut out{Frontier{nullptr, nullptr, 0, nullptr}, nullptr, nullptr, ctx->d_nodes, ctx->d_visited, ctx->d_visited + 1};
-  if (acc == PER_ROOT) {
+  if (ctx->tile_variant == 8 && acc == SINGLE_ROOT) { /* warp-synchronous K2 (PABI_TILE_VARIANT=8) */
+    k_leaf_warp<SINGLE_ROOT><<<grid_for(ctx, n, 32, 1), LEAFW_THREADS, sizeof(LeafWarpBlock), ctx->stream>>>(ctx->dt, in, n, out);
+    LAUNCHED();
+  } else if (acc == PER_ROOT) {
     launch_tile_cfg<TILE_LEAF, PER_ROOT, TileDefault>(ctx, in, 0, n, nullptr, out);
   } else if (acc == WEIGHTED) {
     launch_tile_cfg<TILE_LEAF, WEIGHTED, TileDefault>(ctx, in, 0, n, nullptr, out);
@@ -525,6 +528,7 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     CK(cudaFuncSetAttribute(k_attack_info, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_make_moves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_random_playouts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_leaf_warp<SINGLE_ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeafWarpBlock)));
     CK(cudaFuncSetAttribute(k_moves_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MovesShared)));
     CK(cudaFuncSetAttribute(k_parse_fens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_games_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
@@ -532,7 +536,7 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     CK(cudaFuncSetAttribute(k_games_play_random, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     if (const char* v = std::getenv("PABI_TILE_VARIANT")) {
       ctx->tile_variant = std::atoi(v);
-      if (ctx->tile_variant != 9 && (ctx->tile_variant < 0 || ctx->tile_variant >= TILE_VARIANTS)) ctx->tile_variant = 0;
+      if (ctx->tile_variant != 9 && ctx->tile_variant != 8 && (ctx->tile_variant < 0 || ctx->tile_variant >= TILE_VARIANTS)) ctx->tile_variant = 0;
     }
   } catch (const CudaFail& f) {
     std::fprintf(stderr, "pabi_cuda_create: %s\n", ctx->error.c_str());

@@ -857,4 +857,99 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
   if (LEAF && !MULTI_ROOT) block_add_u64<CFG::THREADS>(acc, block.red, out.nodes);
 }
 
+/* ---- K2, warp-synchronous variant ------------------------------------------------------------
+ * The same three phases as k_tile<TILE_LEAF>, but a tile is 32 parents owned by ONE warp: count +
+ * warp shuffle scan, generation into the warp's private pool, then the 32 lanes walk the pool.  No
+ * block-wide barrier, no idle group while the slowest parent of 256 finishes generating; tiles come
+ * from the ticket counter.  Pool entries are 3 bytes: the move, and kind << 5 | parent.
+ * Measured (B200, startpos perft(8)): 107.8 ms, the same as the block-level kernel with four groups
+ * and tickets (107.8 ms) -- once tiles are scheduled dynamically the barrier waits are hidden by the
+ * other groups and both versions sit on the ALU-pipe limit of count_moves_white.  The block-level kernel
+ * stays the default because it also serves K1 and the per-root / weighted accountings; this one is
+ * selectable with PABI_TILE_VARIANT=8. */
+constexpr int LEAFW_THREADS = 1024;
+constexpr int LEAFW_POOL = 1152; /* entries per warp; 32 parents average ~830 children in the start-position tree */
+
+struct LeafWarpShared {
+  u64 parents[POS_WORDS][32];
+  u16 moves[LEAFW_POOL];
+  u8 tags[LEAFW_POOL];
+};
+struct LeafWarpBlock {
+  SharedTables tables;
+  LeafWarpShared warp[LEAFW_THREADS / 32];
+  u64 red[LEAFW_THREADS / 32];
+};
+
+template <Accounting ACC>
+__global__ void __launch_bounds__(LEAFW_THREADS, 1)
+k_leaf_warp(DeviceTables dt, Frontier in, size_t n, TileOut out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  LeafWarpBlock& block = *reinterpret_cast<LeafWarpBlock*>(smem);
+  stage_tables(&block.tables, dt.image);
+  const Tables tb{&block.tables, dt.g};
+  const int lane = threadIdx.x & 31;
+  LeafWarpShared& sh = block.warp[threadIdx.x >> 5];
+  const size_t n_tiles = (n + 31) / 32;
+  u64 acc = 0;
+  for (;;) {
+    unsigned long long ticket = 0;
+    if (lane == 0) ticket = atomicAdd(out.ticket, 1ULL);
+    const size_t tile = (size_t)__shfl_sync(0xFFFFFFFFu, ticket, 0);
+    if (tile >= n_tiles) break;
+    const size_t i = tile * 32 + lane;
+    const bool valid = i < n;
+    u32 cnt = 0;
+    if (valid) {
+      Pos p = load_pos(in.rec, in.stride, i);
+      cnt = count_moves(p, tb);
+      if (meta_stm(p.meta) == 0) p = mirror(p); /* children are then "white to move" */
+      sh.parents[0][lane] = p.white, sh.parents[1][lane] = p.pawns, sh.parents[2][lane] = p.knights;
+      sh.parents[3][lane] = p.bishops, sh.parents[4][lane] = p.rooks, sh.parents[5][lane] = p.queens;
+      sh.parents[6][lane] = p.kings, sh.parents[7][lane] = p.meta;
+    }
+    u32 inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    const u32 total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    const u32 off = inc - cnt;
+    if (lane == 0 && total) atomicAdd(out.visited, (unsigned long long)total);
+    u64 parent_acc = 0; /* PER_ROOT: nodes below this lane's parent */
+    __syncwarp();
+    for (u32 w = 0; w < total; w += LEAFW_POOL) {
+      if (cnt && off < w + LEAFW_POOL && off + cnt > w) {
+        Pos p;
+        p.white = sh.parents[0][lane], p.pawns = sh.parents[1][lane], p.knights = sh.parents[2][lane], p.bishops = sh.parents[3][lane];
+        p.rooks = sh.parents[4][lane], p.queens = sh.parents[5][lane], p.kings = sh.parents[6][lane], p.meta = sh.parents[7][lane];
+        u32 j = off;
+        generate_moves<1>(p, tb, [&](int from, int to, int promo, int kind) {
+          const u32 slot = j++ - w; /* wraps to a huge value below the window */
+          if (slot < (u32)LEAFW_POOL) sh.moves[slot] = pack_move(from, to, promo), sh.tags[slot] = (u8)(kind << 5 | lane);
+        });
+      }
+      __syncwarp();
+      const u32 end = min(total - w, (u32)LEAFW_POOL);
+      for (u32 c = lane; c < end; c += 32) {
+        const u32 tag = sh.tags[c];
+        const int parent = tag & 31;
+        Pos q;
+        q.white = sh.parents[0][parent], q.pawns = sh.parents[1][parent], q.knights = sh.parents[2][parent];
+        q.bishops = sh.parents[3][parent], q.rooks = sh.parents[4][parent], q.queens = sh.parents[5][parent];
+        q.kings = sh.parents[6][parent], q.meta = sh.parents[7][parent];
+        make_move_kind<1>(q, tb, sh.moves[c], (int)(tag >> 5));
+        const u32 k = count_moves_white(q.white, q.pawns, q.knights, q.bishops, q.rooks, q.queens, q.kings, meta_castling(q.meta) & 3,
+                                        meta_ep(q.meta), tb);
+        if (ACC == PER_ROOT) atomicAdd(out.nodes + in.roots[tile * 32 + parent], (unsigned long long)k);
+        else acc += ACC == WEIGHTED ? k * in.mult[tile * 32 + parent] : (u64)k;
+      }
+      __syncwarp();
+    }
+    (void)parent_acc;
+  }
+  if (ACC != PER_ROOT) block_add_u64<LEAFW_THREADS>(acc, block.red, out.nodes);
+}
+
 } /* namespace pabi */

@@ -97,6 +97,22 @@ def test_hashed_perft_is_exact(pb, engine, small_engine, vectors):
         assert engine.perft_hashed(pb.Position.from_fen(KIWIPETE), d) == [1, 48, 2039, 97862][d]
 
 
+def test_alternative_kernel_geometries_give_the_same_counts(pb, monkeypatch):
+    """PABI_TILE_VARIANT selects other tile geometries of K2 (1..5), the warp-synchronous K2 (8) and the
+    block-level K3 (9); they exist for timing comparisons and must all be exact."""
+    p = pb.Position.from_fen(KIWIPETE)
+    batch = oracle.random_playout(oracle.starting(), 0x5EED0003, 120)
+    want_offsets, want_moves = oracle.generate_moves_batch(batch)
+    for variant in ("1", "2", "3", "4", "5", "8", "9"):
+        monkeypatch.setenv("PABI_TILE_VARIANT", variant)
+        e = pb.Engine(0)
+        assert e.perft(p, 5) == 193690690, variant
+        assert e.perft(pb.Position.starting(), 6) == 119060324, variant
+        offsets, moves = e.generate_moves_batch(batch)
+        assert np.array_equal(offsets, want_offsets) and np.array_equal(moves, want_moves), variant
+        e.close()
+
+
 def test_chunked_search_gives_the_same_counts(pb, small_engine, vectors):
     for case in vectors["perft"]:
         if 100_000 < case["nodes"] < 200_000_000:
