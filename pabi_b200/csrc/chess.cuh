@@ -480,11 +480,14 @@ PB_HD u32 count_moves_white(u64 our, u64 pawns, u64 knights, u64 bishops, u64 ro
 
   /* king steps and castling: the only consumers of the enemy attack map */
   const u64 king_targets = tb.king(king) & ~our;
-  u64 need = king_targets;
-  if (checkers == 0) {
-    if ((rights & 1) && (occ & 0x60ULL) == 0) need |= 0x60ULL;
-    if ((rights & 2) && (occ & 0x0EULL) == 0) need |= 0x0CULL;
+  /* castling walks that are worth checking: right held, not in check, squares between king and rook empty
+   * (position.rs:1226-1288, walk masks attacks.rs:203-214) */
+  u64 castle_walks = 0;
+  if (rights && checkers == 0) {
+    if ((rights & 1) && (occ & 0x60ULL) == 0) castle_walks = 0x60ULL;
+    if ((rights & 2) && (occ & 0x0EULL) == 0) castle_walks |= 0x0CULL;
   }
+  const u64 need = king_targets | castle_walks;
   u32 n = 0;
   if (need) {
     /* `rem` = squares of `need` no enemy piece attacks; it only shrinks, so every later piece is
@@ -501,9 +504,9 @@ PB_HD u32 count_moves_white(u64 our, u64 pawns, u64 knights, u64 bishops, u64 ro
       if (tb.s->orth[sq] & rem) rem &= ~tb.rook(sq, occ_nk);
     }
     n = popc(king_targets & rem);
-    if (checkers == 0) { /* position.rs:1226-1288, walk masks attacks.rs:203-214 */
-      n += ((rights & 1) && (occ & 0x60ULL) == 0 && (rem & 0x60ULL) == 0x60ULL);
-      n += ((rights & 2) && (occ & 0x0EULL) == 0 && (rem & 0x0CULL) == 0x0CULL);
+    if (castle_walks) { /* both squares of a walk must be unattacked */
+      const u64 safe_walks = castle_walks & rem;
+      n += ((safe_walks & 0x60ULL) == 0x60ULL) + ((safe_walks & 0x0CULL) == 0x0CULL);
     }
   }
 
