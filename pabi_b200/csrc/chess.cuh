@@ -465,11 +465,11 @@ PB_HD u64 bswap64(u64 x) {
  * `ep` = en passant square (>= 64: none). */
 template <class TB>
 PB_HD u32 count_moves_white(u64 our, u64 pawns, u64 knights, u64 bishops, u64 rooks, u64 queens, u64 kings, int rights,
-                            int ep, const TB& tb) {
+                            int ep, const TB& tb, int known_king = -1, int known_their_king = -1) {
   const u64 occ = pawns | knights | bishops | rooks | queens | kings;
   const u64 their = occ ^ our;
   const u64 king_bb = kings & our;
-  const int king = lsb(king_bb);
+  const int king = known_king >= 0 ? known_king : lsb(king_bb);
   const u64 their_diag = (bishops | queens) & their;
   const u64 their_orth = (rooks | queens) & their;
 
@@ -493,7 +493,8 @@ PB_HD u32 count_moves_white(u64 our, u64 pawns, u64 knights, u64 bishops, u64 ro
     /* `rem` = squares of `need` no enemy piece attacks; it only shrinks, so every later piece is
      * tested against fewer squares and the scan stops when nothing is left */
     const u64 occ_nk = occ ^ king_bb;
-    u64 rem = need & ~(tb.king(lsb(kings & their)) | pawn_attacks(pawns & their, 1));
+    const int their_king = known_their_king >= 0 ? known_their_king : lsb(kings & their);
+    u64 rem = need & ~(tb.king(their_king) | pawn_attacks(pawns & their, 1));
     for (Squares b(knights & their & tb.s->knight_zone[king]); b.any();) rem &= ~tb.knight(b.pop());
     for (Squares b(their_diag & tb.s->diag_zone[king]); b.any() && rem;) {
       const int sq = b.pop();
@@ -602,6 +603,25 @@ PB_HD Pos mirror(const Pos& p) {
   r.meta = make_meta(((c >> 2) | (c << 2)) & 15, ep < NO_SQUARE ? ep ^ 56 : NO_SQUARE, meta_stm(p.meta) ^ 1,
                      meta_halfmove(p.meta), meta_fullmove(p.meta));
   return r;
+}
+
+/* K2 keeps both king squares in spare bits of the meta word of the parent it holds in shared memory
+ * (bits 48-53: the mover's king, 54-59: the other king), so that the per-child count does not have to
+ * find them again: make_move_kind<US, true> maintains them. */
+constexpr int META_MOVER_KING = 48, META_OTHER_KING = 54;
+PB_HD u64 with_king_squares(const Pos& p) {
+  const u64 occ = p.pawns | p.knights | p.bishops | p.rooks | p.queens | p.kings;
+  const u64 mover = meta_stm(p.meta) == 0 ? p.white : occ & ~p.white;
+  return (p.meta & 0x0000FFFFFFFFFFFFULL) | ((u64)lsb(p.kings & mover) << META_MOVER_KING) |
+         ((u64)lsb(p.kings & ~mover) << META_OTHER_KING);
+}
+
+/* The count for a child produced by make_move_kind<1, true> from a black-to-move parent that carries
+ * its king squares: white to move, our king = the parent's other king. */
+template <class TB>
+PB_HD u32 count_child_white(const Pos& q, const TB& tb) {
+  return count_moves_white(q.white, q.pawns, q.knights, q.bishops, q.rooks, q.queens, q.kings, meta_castling(q.meta) & 3,
+                           meta_ep(q.meta), tb, (int)(q.meta >> META_OTHER_KING) & 63, (int)(q.meta >> META_MOVER_KING) & 63);
 }
 
 /* generate_moves().len() of any position */
@@ -780,7 +800,7 @@ PB_HD void make_move(Pos& p, const TB& tb, u16 mv) {
  * (halfmove, fullmove: position.rs:419,428-430) are not maintained because a count does not
  * read them.  Board, castling rights, en passant square and side to move are exactly those of
  * make_move (checked node by node in tests/test_device_logic_on_host.py). */
-template <int US = -1, class TB>
+template <int US = -1, bool TRACK_KINGS = false, class TB>
 PB_HD void make_move_kind(Pos& p, const TB& tb, u16 mv, int kind) {
   const int from = mv & 63, to = (mv >> 6) & 63, promo = (mv >> 12) & 7;
   const u64 fb = bit(from), tbit = bit(to), m = fb | tbit;
@@ -830,7 +850,12 @@ PB_HD void make_move_kind(Pos& p, const TB& tb, u16 mv, int kind) {
   }
   if (us == 0) white = (white & ~fb) | tbit;
   p.white = white;
-  p.meta = make_meta(castling, ep, us ^ 1, 0, 0);
+  u64 kings_known = 0;
+  if (TRACK_KINGS) { /* bits 48-59 of the parent's meta, the mover's king updated when it moved */
+    kings_known = p.meta & (0xFFFULL << META_MOVER_KING);
+    if (kind == KIND_KING) kings_known = (kings_known & ~(63ULL << META_MOVER_KING)) | ((u64)to << META_MOVER_KING);
+  }
+  p.meta = make_meta(castling, ep, us ^ 1, 0, 0) | kings_known;
 }
 
 /* 64-bit key with the equality semantics of the reference's `Position::hash()` AS MAINTAINED BY

@@ -788,6 +788,7 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
       /* K2 keeps the parent with BLACK to move (mirrored if necessary): every child is then "white
        * to move", which is what count_moves_white wants, and the mover's colour is a constant */
       if (LEAF && meta_stm(p.meta) == 0) p = mirror(p);
+      if (LEAF) p.meta = with_king_squares(p);
       sh.parents[0][tid] = p.white, sh.parents[1][tid] = p.pawns, sh.parents[2][tid] = p.knights;
       sh.parents[3][tid] = p.bishops, sh.parents[4][tid] = p.rooks, sh.parents[5][tid] = p.queens;
       sh.parents[6][tid] = p.kings, sh.parents[7][tid] = p.meta;
@@ -834,9 +835,8 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         const int parent = (e >> 16) & 0xFFF;
         Pos q = tile_parent(sh, parent);
         if (LEAF) {
-          make_move_kind<1>(q, tb, (u16)(e & 0xFFFF), (int)(e >> 28));
-          const u32 k = count_moves_white(q.white, q.pawns, q.knights, q.bishops, q.rooks, q.queens, q.kings,
-                                          meta_castling(q.meta) & 3, meta_ep(q.meta), tb);
+          make_move_kind<1, true>(q, tb, (u16)(e & 0xFFFF), (int)(e >> 28));
+          const u32 k = count_child_white(q, tb);
           if (MULTI_ROOT) atomicAdd(&sh.parent_nodes[parent], k);
           else acc += ACC == WEIGHTED ? k * in.mult[first + tile * PARENTS + parent] : (u64)k;
         } else {
@@ -904,6 +904,7 @@ k_leaf_warp(DeviceTables dt, Frontier in, size_t n, TileOut out) {
       Pos p = load_pos(in.rec, in.stride, i);
       cnt = count_moves(p, tb);
       if (meta_stm(p.meta) == 0) p = mirror(p); /* children are then "white to move" */
+      p.meta = with_king_squares(p);
       sh.parents[0][lane] = p.white, sh.parents[1][lane] = p.pawns, sh.parents[2][lane] = p.knights;
       sh.parents[3][lane] = p.bishops, sh.parents[4][lane] = p.rooks, sh.parents[5][lane] = p.queens;
       sh.parents[6][lane] = p.kings, sh.parents[7][lane] = p.meta;
@@ -939,9 +940,8 @@ k_leaf_warp(DeviceTables dt, Frontier in, size_t n, TileOut out) {
         q.white = sh.parents[0][parent], q.pawns = sh.parents[1][parent], q.knights = sh.parents[2][parent];
         q.bishops = sh.parents[3][parent], q.rooks = sh.parents[4][parent], q.queens = sh.parents[5][parent];
         q.kings = sh.parents[6][parent], q.meta = sh.parents[7][parent];
-        make_move_kind<1>(q, tb, sh.moves[c], (int)(tag >> 5));
-        const u32 k = count_moves_white(q.white, q.pawns, q.knights, q.bishops, q.rooks, q.queens, q.kings, meta_castling(q.meta) & 3,
-                                        meta_ep(q.meta), tb);
+        make_move_kind<1, true>(q, tb, sh.moves[c], (int)(tag >> 5));
+        const u32 k = count_child_white(q, tb);
         if (ACC == PER_ROOT) atomicAdd(out.nodes + in.roots[tile * 32 + parent], (unsigned long long)k);
         else acc += ACC == WEIGHTED ? k * in.mult[tile * 32 + parent] : (u64)k;
       }

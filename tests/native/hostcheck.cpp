@@ -72,15 +72,15 @@ static uint64_t perft_rec(const Pos& p, const Tables& tb, int depth) {
   int kinds[256];
   uint32_t k = 0;
   if (depth == 2) { /* the path of k_tile<LEAF>: parent mirrored to black-to-move, children counted as white */
-    const Pos b = meta_stm(p.meta) == 0 ? mirror(p) : p;
+    Pos b = meta_stm(p.meta) == 0 ? mirror(p) : p;
+    b.meta = with_king_squares(b);
     generate_moves<1>(b, tb, [&](int f, int t, int pr, int kind) { kinds[k] = kind, moves[k++] = pack_move(f, t, pr); });
     if (k != count_moves(p, tb)) return ~0ULL;
     uint64_t n = 0;
     for (uint32_t i = 0; i < k; i++) {
       Pos c = b;
-      make_move_kind<1>(c, tb, moves[i], kinds[i]);
-      n += count_moves_white(c.white, c.pawns, c.knights, c.bishops, c.rooks, c.queens, c.kings, meta_castling(c.meta) & 3,
-                             meta_ep(c.meta), tb);
+      make_move_kind<1, true>(c, tb, moves[i], kinds[i]);
+      n += count_child_white(c, tb);
     }
     return n;
   }
