@@ -1,0 +1,209 @@
+/*
+ * incremental.cuh -- the "quiet move" fast path of the fused last-two-plies kernel (K2).
+ *
+ * perft spends its time counting the replies to every move of every parent of the last ply but
+ * one.  For most moves the reply count can be derived from a per-parent context instead of being
+ * recomputed: if the mover S plays a quiet move whose from- and to-square touch neither a line of
+ * the replying side T's king nor the attack set of any T slider, then
+ *   - T is not in check and none of its pieces becomes (un)pinned,
+ *   - every T knight / bishop / rook / queen has exactly the moves it would have had in the
+ *     parent position (the vacated square was a capture target and is now a quiet target, the
+ *     occupied square the other way round),
+ * so  replies = base(parent) + T's pawn moves + T's king moves, where only the last two depend on
+ * the move.  Everything here is in K2's normalised frame: the parent is stored with BLACK (S) to
+ * move, T is white.  A move that does not qualify ("other") takes the full path
+ * (make_move_kind + count_child_white); the split is decided per target set in the parent's thread,
+ * so both kinds of children are processed by full warps.
+ *
+ * Exactness is tested in tests/test_device_logic_on_host.py: for every node of the reference
+ * trees every move classified as quiet-clean has fast count == full count.
+ */
+#pragma once
+#include "chess.cuh"
+
+namespace pabi {
+
+/* per-parent context, carried in the shared-memory parent record: `base` in meta bits 32-47 (the
+ * fullmove counter is not needed in K2), `guard` in a side array */
+constexpr int META_BASE = 32;
+
+struct TContext {
+  u64 guard; /* squares a clean move may not touch: T-king lines and T slider attack sets; ~0 = no clean moves */
+  u32 base;  /* moves of T's knights, bishops, rooks and queens in the parent position */
+};
+
+template <class TB>
+PB_HD TContext t_context(const Pos& n, const TB& tb) {
+  const u64 occ = n.pawns | n.knights | n.bishops | n.rooks | n.queens | n.kings;
+  const u64 W = n.white, B = occ ^ W;
+  const int tk = lsb(n.kings & W);
+  const u64 s_diag = (n.bishops | n.queens) & B, s_orth = (n.rooks | n.queens) & B;
+  const u64 kd = tb.bishop(tk, occ), ko = tb.rook(tk, occ);
+  TContext c{~0ULL, 0};
+  /* T in check (cannot happen when S is to move in a legal position) or T pieces pinned: no fast path */
+  if ((tb.knight(tk) & n.knights & B) | (pawn_attacks(n.kings & W, 0) & n.pawns & B) | (kd & s_diag) | (ko & s_orth)) return c;
+  {
+    const u64 cand = kd & W;
+    if (cand && (tb.bishop(tk, occ ^ cand) & ~kd & s_diag)) return c;
+  }
+  {
+    const u64 cand = ko & W;
+    if (cand && (tb.rook(tk, occ ^ cand) & ~ko & s_orth)) return c;
+  }
+  const u64 not_w = ~W;
+  u64 reach = 0;
+  u32 base = 0;
+  for (Squares b(n.knights & W); b.any();) base += popc(tb.knight(b.pop()) & not_w);
+  for (Squares b((n.rooks | n.queens) & W); b.any();) {
+    const u64 a = tb.rook(b.pop(), occ);
+    reach |= a;
+    base += popc(a & not_w);
+  }
+  for (Squares b((n.bishops | n.queens) & W); b.any();) {
+    const u64 a = tb.bishop(b.pop(), occ);
+    reach |= a;
+    base += popc(a & not_w);
+  }
+  c.guard = reach | tb.s->orth[tk] | tb.s->diag[tk] | tb.s->anti[tk];
+  c.base = base;
+  return c;
+}
+
+/* S's legal moves (black to move) as target sets split into clean and other.  Sink:
+ *   piece(from, kind, clean_targets, other_targets)   non-pawn moves (no promotion)
+ *   pushes(clean_to, other_to, delta)                 pawn pushes, from = to + delta; other_to on rank 1 promote
+ *   pawn_capture(from, to)                            promotes when `to` is on rank 1
+ *   en_passant(from, to)
+ *   castle(from, to)
+ * The union of everything reported is exactly generate_moves(n). */
+template <class TB, class Sink>
+PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 guard, Sink& sink) {
+  Analysis a;
+  analyze<1>(n, tb, a);
+  sink.piece(a.king, KIND_KING, 0, a.safe_king);
+  if (a.block == 0) return;
+  const u64 targets = ~a.our & a.block;
+  const u64 W = a.their;
+  const u64 tk_bb = n.kings & W;
+  const int tk = lsb(tk_bb);
+  const u64 open = ~guard & ~W; /* a clean move lands on an empty square outside the guard */
+
+  for (Squares b(n.knights & a.our & ~a.pins); b.any();) {
+    const int from = b.pop();
+    const u64 t = tb.knight(from) & targets;
+    const u64 c = (guard >> from) & 1 ? 0 : t & open & ~tb.knight(tk); /* a knight on KNIGHT[tk] checks */
+    sink.piece(from, KIND_KNIGHT, c, t & ~c);
+  }
+  for (Squares b((n.rooks | n.queens) & a.our); b.any();) {
+    const int from = b.pop();
+    u64 t = tb.rook(from, a.occ) & targets;
+    if ((a.pins >> from) & 1) t &= tb.line(a.king, from);
+    const u64 c = (guard >> from) & 1 ? 0 : t & open; /* off the king's lines a slider cannot check */
+    sink.piece(from, (n.queens >> from) & 1 ? KIND_QUEEN : KIND_ROOK, c, t & ~c);
+  }
+  for (Squares b((n.bishops | n.queens) & a.our); b.any();) {
+    const int from = b.pop();
+    u64 t = tb.bishop(from, a.occ) & targets;
+    if ((a.pins >> from) & 1) t &= tb.line(a.king, from);
+    const u64 c = (guard >> from) & 1 ? 0 : t & open;
+    sink.piece(from, (n.queens >> from) & 1 ? KIND_QUEEN : KIND_BISHOP, c, t & ~c);
+  }
+
+  /* pawns of the mover (black, moving down the board) */
+  const PawnSets ps = pawn_sources(n, tb, a);
+  const u64 capture_targets = W & a.block;
+  for (Squares b(ps.west | ps.east); b.any();) {
+    const int from = b.pop();
+    const u64 from_bb = bit(from);
+    const u64 t = (pawn_attacks_west(from_bb & ps.west, 1) | pawn_attacks_east(from_bb & ps.east, 1)) & capture_targets;
+    for (Squares ts(t); ts.any();) sink.pawn_capture(from, ts.pop());
+  }
+  if (meta_ep(n.meta) < NO_SQUARE)
+    for (Squares b(en_passant_sources(n, tb, a)); b.any();) sink.en_passant(b.pop(), meta_ep(n.meta));
+  const u64 empty = ~a.occ;
+  const u64 single_all = (ps.pushers >> 8) & empty;
+  const u64 single = single_all & a.block;
+  const u64 dbl = ((single_all & RANK_6) >> 8) & empty & a.block;
+  const u64 checks = pawn_attacks(tk_bb, 0);            /* squares from which a black pawn attacks T's king */
+  const u64 t_pawns = n.pawns & W;
+  const u64 beside_t_pawn = ((t_pawns & ~FILE_A) >> 1) | ((t_pawns & ~FILE_H) << 1); /* a double push there creates an en passant square */
+  const u64 c1 = single & open & ~(guard >> 8) & ~RANK_1 & ~checks;
+  const u64 c2 = dbl & open & ~(guard >> 16) & ~checks & ~beside_t_pawn;
+  sink.pushes(c1, single & ~c1, 8);
+  sink.pushes(c2, dbl & ~c2, 16);
+  const int c = castle_moves(n, a);
+  if (c & 1) sink.castle(60, 62);
+  if (c & 2) sink.castle(60, 58);
+}
+
+/* (clean, other) move counts of a parent: the sizing pass of the split pool */
+struct SplitCounter {
+  u32 clean = 0, other = 0;
+  PB_HD void piece(int, int, u64 c, u64 o) { clean += popc(c), other += popc(o); }
+  PB_HD void pushes(u64 c, u64 o, int) { clean += popc(c), other += popc(o) + 3 * popc(o & RANK_1); }
+  PB_HD void pawn_capture(int, int to) { other += to < 8 ? 4 : 1; }
+  PB_HD void en_passant(int, int) { ++other; }
+  PB_HD void castle(int, int) { ++other; }
+};
+
+/* king steps + castling of a white-to-move position that is not in check (the `need` / `rem` scan of
+ * count_moves_white) */
+template <class TB>
+PB_HD u32 king_part_white(u64 our, u64 their, u64 occ, u64 pawns, u64 knights, u64 diag_sliders, u64 orth_sliders, int rights, int king,
+                          int their_king, const TB& tb) {
+  const u64 king_targets = tb.king(king) & ~our;
+  u64 castle_walks = 0;
+  if (rights) {
+    if ((rights & 1) && (occ & 0x60ULL) == 0) castle_walks = 0x60ULL;
+    if ((rights & 2) && (occ & 0x0EULL) == 0) castle_walks |= 0x0CULL;
+  }
+  const u64 need = king_targets | castle_walks;
+  if (!need) return 0;
+  const u64 occ_nk = occ ^ bit(king);
+  u64 rem = need & ~(tb.king(their_king) | pawn_attacks(pawns & their, 1));
+  for (Squares b(knights & their & tb.s->knight_zone[king]); b.any();) rem &= ~tb.knight(b.pop());
+  for (Squares b(diag_sliders & their & tb.s->diag_zone[king]); b.any() && rem;) {
+    const int sq = b.pop();
+    if ((tb.s->diag[sq] | tb.s->anti[sq]) & rem) rem &= ~tb.bishop(sq, occ_nk);
+  }
+  for (Squares b(orth_sliders & their & tb.s->orth_zone[king]); b.any() && rem;) {
+    const int sq = b.pop();
+    if (tb.s->orth[sq] & rem) rem &= ~tb.rook(sq, occ_nk);
+  }
+  u32 n = popc(king_targets & rem);
+  if (castle_walks) {
+    const u64 safe_walks = castle_walks & rem;
+    n += ((safe_walks & 0x60ULL) == 0x60ULL) + ((safe_walks & 0x0CULL) == 0x0CULL);
+  }
+  return n;
+}
+
+/* Replies to a clean move: n = the normalised parent (black to move; meta carries base and both king
+ * squares), the move is quiet, by a pawn, knight, bishop, rook or queen. */
+template <class TB>
+PB_HD u32 count_child_fast(const Pos& n, const TB& tb, int from, int to, int kind) {
+  const u64 m = bit(from) | bit(to);
+  u64 pawns = n.pawns, knights = n.knights, bishops = n.bishops, rooks = n.rooks, queens = n.queens;
+  if (kind == KIND_PAWN) pawns ^= m;
+  else if (kind == KIND_KNIGHT) knights ^= m;
+  else if (kind == KIND_BISHOP) bishops ^= m;
+  else if (kind == KIND_ROOK) rooks ^= m;
+  else queens ^= m;
+  const u64 W = n.white;
+  const u64 occ = pawns | knights | bishops | rooks | queens | n.kings;
+  const u64 their = occ ^ W;
+  const int king = (int)(n.meta >> META_OTHER_KING) & 63, their_king = (int)(n.meta >> META_MOVER_KING) & 63;
+  u32 cnt = (u32)(n.meta >> META_BASE) & 0xFFFF;
+  cnt += king_part_white(W, their, occ, pawns, knights, bishops | queens, rooks | queens, meta_castling(n.meta) & 3, king, their_king, tb);
+  /* T's pawns: nothing pinned, no check, no en passant square (position.rs:1106-1224 set-wise) */
+  const u64 wp = pawns & W;
+  const u64 west = ((wp & ~FILE_A) << 7) & their;
+  const u64 east = ((wp & ~FILE_H) << 9) & their;
+  const u64 single = (wp << 8) & ~occ;
+  const u64 dbl = ((single & RANK_3) << 8) & ~occ;
+  cnt += popc(west) + popc(east) + popc(single) + popc(dbl);
+  if ((west | east | single) & RANK_8) cnt += 3 * (popc(west & RANK_8) + popc(east & RANK_8) + popc(single & RANK_8));
+  return cnt;
+}
+
+} /* namespace pabi */

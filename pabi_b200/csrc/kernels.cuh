@@ -18,6 +18,7 @@
 
 #include "chess.cuh"
 #include "fen.cuh"
+#include "incremental.cuh"
 
 namespace pabi {
 
@@ -717,6 +718,7 @@ struct TileGroupShared {
   u32 parent_nodes[CFG::PARENTS]; /* K2, multi-root: nodes below each parent */
   u32 warp_sums[CFG::GROUP_THREADS / 32 + 1];
   unsigned long long next_tile; /* TILE_LEAF: the tile this group took from the ticket counter */
+  u64 guard[CFG::PARENTS];      /* TILE_LEAF: TContext::guard of each parent (incremental.cuh) */
 };
 
 template <class CFG>
@@ -747,6 +749,42 @@ struct TileOut {
   unsigned long long* nodes;        /* TILE_LEAF: per-root (or single) leaf counts */
   unsigned long long* visited;      /* TILE_LEAF statistics: children generated */
   unsigned long long* ticket;       /* TILE_LEAF: tiles are handed out dynamically (zeroed before the launch) */
+};
+
+/* enumerate_split sink of K2's phase A: clean moves go to pool[clean_at ...), the others to
+ * pool[other_at ...); `lo` is the start of the current pool window (slots below it wrap to huge values) */
+struct SplitEmitter {
+  u32* pool;
+  u32 clean_at, other_at, lo, cap, tag; /* tag = parent << 16 */
+  __device__ __forceinline__ void put(u32& at, int from, int to, int promo, int kind) {
+    const u32 slot = at++ - lo;
+    if (slot < cap) pool[slot] = ((u32)kind << 28) | tag | pack_move(from, to, promo);
+  }
+  __device__ __forceinline__ void other(int from, int to, int kind) {
+    if (kind == KIND_PAWN && to < 8) { /* black promotes on rank 1 */
+      put(other_at, from, to, PROMO_Q, kind), put(other_at, from, to, PROMO_R, kind);
+      put(other_at, from, to, PROMO_B, kind), put(other_at, from, to, PROMO_N, kind);
+    } else {
+      put(other_at, from, to, 0, kind);
+    }
+  }
+  __device__ __forceinline__ void piece(int from, int kind, u64 c, u64 o) {
+    for (Squares t(c); t.any();) put(clean_at, from, t.pop(), 0, kind);
+    for (Squares t(o); t.any();) put(other_at, from, t.pop(), 0, kind);
+  }
+  __device__ __forceinline__ void pushes(u64 c, u64 o, int delta) {
+    for (Squares t(c); t.any();) {
+      const int to = t.pop();
+      put(clean_at, to + delta, to, 0, KIND_PAWN);
+    }
+    for (Squares t(o); t.any();) {
+      const int to = t.pop();
+      other(to + delta, to, KIND_PAWN);
+    }
+  }
+  __device__ __forceinline__ void pawn_capture(int from, int to) { other(from, to, KIND_PAWN); }
+  __device__ __forceinline__ void en_passant(int from, int to) { put(other_at, from, to, 0, KIND_PAWN); }
+  __device__ __forceinline__ void castle(int from, int to) { put(other_at, from, to, 0, KIND_KING); }
 };
 
 /* In TILE_EXPAND / TILE_MOVES the per-parent counts come from the global scan (`prefix`, built by
@@ -781,21 +819,32 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
     const size_t i = tile * PARENTS + tid;
     const bool valid = tid < PARENTS && i < n;
     u32 cnt = 0, off = 0, total;
+    u32 clean_total = 0; /* K2: the first clean_total children of the tile take the fast path */
     u64 out_base = 0; /* global index of this tile's first child / move */
     if (valid) {
       Pos p = load_pos(in.rec, in.stride, first + i);
-      if (LEAF) cnt = count_moves(p, tb);
-      /* K2 keeps the parent with BLACK to move (mirrored if necessary): every child is then "white
-       * to move", which is what count_moves_white wants, and the mover's colour is a constant */
-      if (LEAF && meta_stm(p.meta) == 0) p = mirror(p);
-      if (LEAF) p.meta = with_king_squares(p);
+      if (LEAF) {
+        /* K2 keeps the parent with BLACK to move (mirrored if necessary): every child is then "white
+         * to move", which is what count_moves_white wants, and the mover's colour is a constant.  The
+         * record also carries the king squares and the per-parent context of the quiet-move fast path;
+         * cnt packs (other << 16 | clean) move counts for one scan. */
+        if (meta_stm(p.meta) == 0) p = mirror(p);
+        const TContext ctx = t_context(p, tb);
+        p.meta = (with_king_squares(p) & ~(0xFFFFULL << META_BASE)) | ((u64)ctx.base << META_BASE);
+        sh.guard[tid] = ctx.guard;
+        SplitCounter counter;
+        enumerate_split(p, tb, ctx.guard, counter);
+        cnt = counter.other << 16 | counter.clean;
+      }
       sh.parents[0][tid] = p.white, sh.parents[1][tid] = p.pawns, sh.parents[2][tid] = p.knights;
       sh.parents[3][tid] = p.bishops, sh.parents[4][tid] = p.rooks, sh.parents[5][tid] = p.queens;
       sh.parents[6][tid] = p.kings, sh.parents[7][tid] = p.meta;
     }
     if (LEAF) {
       if (MULTI_ROOT && tid < PARENTS) sh.parent_nodes[tid] = 0;
-      off = block_exclusive_scan<GT, SYNC>(cnt, sh.warp_sums, total, tid, group);
+      off = block_exclusive_scan<GT, SYNC>(cnt, sh.warp_sums, total, tid, group); /* both halves: < 2^16 per tile */
+      clean_total = total & 0xFFFF;
+      total = clean_total + (total >> 16);
       if (tid == 0 && total) atomicAdd(out.visited, (unsigned long long)total); /* statistics: positions at the last ply but one */
     } else {
       const size_t tile_first = first + tile * PARENTS;
@@ -816,10 +865,17 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
     }
 
     for (u32 w = 0; w < total; w += POOL) {
-      if (cnt && off < w + POOL && off + cnt > w) {
+      if (LEAF) {
+        /* clean children occupy [0, clean_total) of the tile, the others follow */
+        const u32 c0 = off & 0xFFFF, c1 = c0 + (cnt & 0xFFFF), o0 = clean_total + (off >> 16), o1 = o0 + (cnt >> 16);
+        if (cnt && ((c0 < w + POOL && c1 > w) || (o0 < w + POOL && o1 > w))) {
+          SplitEmitter emit{sh.pool, c0, o0, w, (u32)POOL, (u32)tid << 16};
+          enumerate_split(tile_parent(sh, tid), tb, sh.guard[tid], emit);
+        }
+      } else if (cnt && off < w + POOL && off + cnt > w) {
         u32 j = off;
         /* the parent is re-read from shared memory so that it does not occupy registers during phase B */
-        generate_moves<LEAF ? 1 : -1>(tile_parent(sh, tid), tb, [&](int from, int to, int promo, int kind) {
+        generate_moves(tile_parent(sh, tid), tb, [&](int from, int to, int promo, int kind) {
           const u32 slot = j++ - w; /* wraps to a huge value below the window */
           if (slot < (u32)POOL) sh.pool[slot] = ((u32)kind << 28) | ((u32)tid << 16) | pack_move(from, to, promo);
         });
@@ -835,8 +891,13 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         const int parent = (e >> 16) & 0xFFF;
         Pos q = tile_parent(sh, parent);
         if (LEAF) {
-          make_move_kind<1, true>(q, tb, (u16)(e & 0xFFFF), (int)(e >> 28));
-          const u32 k = count_child_white(q, tb);
+          u32 k;
+          if (w + c < clean_total) { /* quiet move off every line that matters: replies = base + pawns + king */
+            k = count_child_fast(q, tb, (int)(e & 63), (int)((e >> 6) & 63), (int)(e >> 28));
+          } else {
+            make_move_kind<1, true>(q, tb, (u16)(e & 0xFFFF), (int)(e >> 28));
+            k = count_child_white(q, tb);
+          }
           if (MULTI_ROOT) atomicAdd(&sh.parent_nodes[parent], k);
           else acc += ACC == WEIGHTED ? k * in.mult[first + tile * PARENTS + parent] : (u64)k;
         } else {

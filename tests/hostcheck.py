@@ -28,6 +28,7 @@ def lib() -> C.CDLL:
         L.hostcheck_analysis.argtypes = [P, C.POINTER(C.c_uint64)]
         L.hostcheck_attack_info.argtypes = [P, C.POINTER(C.c_uint64)]
         L.hostcheck_parse.argtypes = [C.c_char_p, C.c_size_t, P]
+        L.hostcheck_incremental.argtypes = [P, C.c_int, C.POINTER(C.c_uint64)]
         L.hostcheck_perft.restype = C.c_uint64
         L.hostcheck_perft.argtypes = [P, C.c_int]
         L.hostcheck_walk_compare.restype = C.c_uint64

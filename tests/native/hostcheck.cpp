@@ -6,8 +6,11 @@
  * without a GPU.  Never linked into libpabi_b200.so.
  */
 #include "../../pabi_b200/csrc/fen.cuh"
+#include "../../pabi_b200/csrc/incremental.cuh"
 #include "../../pabi_b200/csrc/record.h"
 #include "../../pabi_b200/csrc/tables.h"
+
+#include <algorithm>
 
 using namespace pabi;
 
@@ -148,6 +151,96 @@ uint64_t hostcheck_walk_compare(const pabi_position_t* root, int depth, oracle_g
   uint64_t bad = walk_compare(*root, depth, gen, mk, first_bad, &v);
   if (visited) *visited = v;
   return bad;
+}
+
+/* incremental.cuh: for every node of the tree as a parent, every move classified clean must have
+ * fast count == full count, the split must cover exactly the generated moves, and the counting sink
+ * must agree with what is enumerated.  out[0] parents, out[1] moves, out[2] clean moves, out[3] mismatches. */
+struct CheckSink {
+  const Pos& n;
+  const Tables& tb;
+  uint64_t* out;
+  uint32_t clean = 0, other = 0;
+  uint16_t moves[512];
+  uint32_t k = 0;
+  void full(int from, int to, int promo, int kind) {
+    ++other;
+    moves[k++] = pack_move(from, to, promo);
+    (void)kind;
+  }
+  void piece(int from, int kind, u64 c, u64 o) {
+    for (Squares t(c); t.any();) {
+      const int to = t.pop();
+      ++clean;
+      moves[k++] = pack_move(from, to, 0);
+      Pos ch = n;
+      make_move_kind<1, true>(ch, tb, pack_move(from, to, 0), kind);
+      if (count_child_fast(n, tb, from, to, kind) != count_child_white(ch, tb)) ++out[3];
+    }
+    for (Squares t(o); t.any();) full(from, t.pop(), 0, kind);
+  }
+  void pushes(u64 c, u64 o, int delta) {
+    piece_pawn(c, delta);
+    for (Squares t(o); t.any();) {
+      const int to = t.pop();
+      if (to < 8) for (int pr = 4; pr >= 1; pr--) full(to + delta, to, pr, KIND_PAWN);
+      else full(to + delta, to, 0, KIND_PAWN);
+    }
+  }
+  void piece_pawn(u64 c, int delta) {
+    for (Squares t(c); t.any();) {
+      const int to = t.pop();
+      ++clean;
+      moves[k++] = pack_move(to + delta, to, 0);
+      Pos ch = n;
+      make_move_kind<1, true>(ch, tb, pack_move(to + delta, to, 0), KIND_PAWN);
+      if (count_child_fast(n, tb, to + delta, to, KIND_PAWN) != count_child_white(ch, tb)) ++out[3];
+    }
+  }
+  void pawn_capture(int from, int to) {
+    if (to < 8) for (int pr = 4; pr >= 1; pr--) full(from, to, pr, KIND_PAWN);
+    else full(from, to, 0, KIND_PAWN);
+  }
+  void en_passant(int from, int to) { full(from, to, 0, KIND_PAWN); }
+  void castle(int from, int to) { full(from, to, 0, KIND_KING); }
+};
+
+static void incremental_walk(const Pos& p, const Tables& tb, int depth, uint64_t* out) {
+  Pos n = meta_stm(p.meta) == 0 ? mirror(p) : p;
+  const TContext ctx = t_context(n, tb);
+  n.meta = (with_king_squares(n) & ~(0xFFFFULL << META_BASE)) | ((u64)ctx.base << META_BASE);
+  CheckSink sink{n, tb, out};
+  enumerate_split(n, tb, ctx.guard, sink);
+  SplitCounter counter;
+  enumerate_split(n, tb, ctx.guard, counter);
+  ++out[0], out[1] += sink.k, out[2] += sink.clean;
+  if (counter.clean != sink.clean || counter.other != sink.other) ++out[3];
+  /* the split covers exactly the legal moves */
+  uint16_t want[256];
+  uint32_t nw = 0;
+  generate_moves<1>(n, tb, [&](int f, int t, int pr, int) { want[nw++] = pack_move(f, t, pr); });
+  if (nw != sink.k) ++out[3];
+  else {
+    std::sort(want, want + nw);
+    std::sort(sink.moves, sink.moves + sink.k);
+    for (uint32_t i = 0; i < nw; i++)
+      if (want[i] != sink.moves[i]) { ++out[3]; break; }
+  }
+  if (depth == 0) return;
+  uint16_t mv[256];
+  int kinds[256];
+  uint32_t k = 0;
+  generate_moves(p, tb, [&](int f, int t, int pr, int kind) { kinds[k] = kind, mv[k++] = pack_move(f, t, pr); });
+  for (uint32_t i = 0; i < k; i++) {
+    Pos c = p;
+    make_move(c, tb, mv[i]);
+    incremental_walk(c, tb, depth - 1, out);
+  }
+}
+
+void hostcheck_incremental(const pabi_position_t* root, int depth, uint64_t out[4]) {
+  out[0] = out[1] = out[2] = out[3] = 0;
+  incremental_walk(pack_record(*root), host_tb(), depth, out);
 }
 
 /* table access for tests/test_tables*.py */
