@@ -28,9 +28,20 @@ namespace pabi {
 constexpr int META_BASE = 32;
 
 struct TContext {
-  u64 guard; /* squares a clean move may not touch: T-king lines and T slider attack sets; ~0 = no clean moves */
+  u64 reach; /* union of T's slider attack sets: a clean move neither leaves nor lands on it; ~0 = no clean moves */
   u32 base;  /* moves of T's knights, bishops, rooks and queens in the parent position */
 };
+
+/* The squares on the rays from T's king up to and including the SECOND piece of each ray.  Only there
+ * can a move change who checks or pins: a piece leaving (it is the first or second blocker of the ray)
+ * or a slider arriving (it sees the king, or pins the single blocker).  Farther out at least two pieces
+ * shield the king whatever happens to a third, and a knight or pawn arriving on a ray changes nothing. */
+template <class TB>
+PB_HD u64 king_guard(const Pos& n, const TB& tb, int tk) {
+  const u64 occ = n.pawns | n.knights | n.bishops | n.rooks | n.queens | n.kings;
+  const u64 kd = tb.bishop(tk, occ), ko = tb.rook(tk, occ);
+  return tb.bishop(tk, occ & ~kd) | tb.rook(tk, occ & ~ko);
+}
 
 template <class TB>
 PB_HD TContext t_context(const Pos& n, const TB& tb) {
@@ -64,7 +75,7 @@ PB_HD TContext t_context(const Pos& n, const TB& tb) {
     reach |= a;
     base += popc(a & not_w);
   }
-  c.guard = reach | tb.s->orth[tk] | tb.s->diag[tk] | tb.s->anti[tk];
+  c.reach = reach;
   c.base = base;
   return c;
 }
@@ -77,7 +88,7 @@ PB_HD TContext t_context(const Pos& n, const TB& tb) {
  *   castle(from, to)
  * The union of everything reported is exactly generate_moves(n). */
 template <class TB, class Sink>
-PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 guard, Sink& sink) {
+PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 reach, Sink& sink) {
   Analysis a;
   analyze<1>(n, tb, a);
   sink.piece(a.king, KIND_KING, 0, a.safe_king);
@@ -86,12 +97,15 @@ PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 guard, Sink& sink) {
   const u64 W = a.their;
   const u64 tk_bb = n.kings & W;
   const int tk = lsb(tk_bb);
-  const u64 open = ~guard & ~W; /* a clean move lands on an empty square outside the guard */
+  /* a clean move leaves a square outside `guard`; a slider lands outside `guard`, a knight or pawn outside `reach` */
+  const u64 guard = reach == ~0ULL ? reach : reach | king_guard(n, tb, tk);
+  const u64 open = ~guard & ~W;
+  const u64 open_leaper = ~reach & ~W;
 
   for (Squares b(n.knights & a.our & ~a.pins); b.any();) {
     const int from = b.pop();
     const u64 t = tb.knight(from) & targets;
-    const u64 c = (guard >> from) & 1 ? 0 : t & open & ~tb.knight(tk); /* a knight on KNIGHT[tk] checks */
+    const u64 c = (guard >> from) & 1 ? 0 : t & open_leaper & ~tb.knight(tk); /* a knight on KNIGHT[tk] checks */
     sink.piece(from, KIND_KNIGHT, c, t & ~c);
   }
   for (Squares b((n.rooks | n.queens) & a.our); b.any();) {
@@ -127,8 +141,8 @@ PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 guard, Sink& sink) {
   const u64 checks = pawn_attacks(tk_bb, 0);            /* squares from which a black pawn attacks T's king */
   const u64 t_pawns = n.pawns & W;
   const u64 beside_t_pawn = ((t_pawns & ~FILE_A) >> 1) | ((t_pawns & ~FILE_H) << 1); /* a double push there creates an en passant square */
-  const u64 c1 = single & open & ~(guard >> 8) & ~RANK_1 & ~checks;
-  const u64 c2 = dbl & open & ~(guard >> 16) & ~checks & ~beside_t_pawn;
+  const u64 c1 = single & open_leaper & ~(guard >> 8) & ~RANK_1 & ~checks;
+  const u64 c2 = dbl & open_leaper & ~(guard >> 16) & ~checks & ~beside_t_pawn;
   sink.pushes(c1, single & ~c1, 8);
   sink.pushes(c2, dbl & ~c2, 16);
   const int c = castle_moves(n, a);

@@ -718,7 +718,7 @@ struct TileGroupShared {
   u32 parent_nodes[CFG::PARENTS]; /* K2, multi-root: nodes below each parent */
   u32 warp_sums[CFG::GROUP_THREADS / 32 + 1];
   unsigned long long next_tile; /* TILE_LEAF: the tile this group took from the ticket counter */
-  u64 guard[CFG::PARENTS];      /* TILE_LEAF: TContext::guard of each parent (incremental.cuh) */
+  u64 guard[CFG::PARENTS];      /* TILE_LEAF: TContext::reach of each parent (incremental.cuh) */
 };
 
 template <class CFG>
@@ -831,9 +831,9 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         if (meta_stm(p.meta) == 0) p = mirror(p);
         const TContext ctx = t_context(p, tb);
         p.meta = (with_king_squares(p) & ~(0xFFFFULL << META_BASE)) | ((u64)ctx.base << META_BASE);
-        sh.guard[tid] = ctx.guard;
+        sh.guard[tid] = ctx.reach;
         SplitCounter counter;
-        enumerate_split(p, tb, ctx.guard, counter);
+        enumerate_split(p, tb, ctx.reach, counter);
         cnt = counter.other << 16 | counter.clean;
       }
       sh.parents[0][tid] = p.white, sh.parents[1][tid] = p.pawns, sh.parents[2][tid] = p.knights;
