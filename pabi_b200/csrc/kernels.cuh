@@ -719,6 +719,8 @@ struct TileGroupShared {
   u32 warp_sums[CFG::GROUP_THREADS / 32 + 1];
   unsigned long long next_tile; /* TILE_LEAF: the tile this group took from the ticket counter */
   u64 guard[CFG::PARENTS];      /* TILE_LEAF: TContext::reach of each parent (incremental.cuh) */
+  u32 offs[CFG::PARENTS + 1];   /* TILE_LEAF: packed exclusive prefix (other << 16 | clean) of the parents' move counts */
+  u32 chunk;                    /* TILE_LEAF: parents per pool filling */
 };
 
 template <class CFG>
@@ -864,35 +866,48 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
       group_sync<SYNC>(group); /* the parents are in shared memory */
     }
 
-    for (u32 w = 0; w < total; w += POOL) {
-      if (LEAF) {
-        /* clean children occupy [0, clean_total) of the tile, the others follow */
-        const u32 c0 = off & 0xFFFF, c1 = c0 + (cnt & 0xFFFF), o0 = clean_total + (off >> 16), o1 = o0 + (cnt >> 16);
-        if (cnt && ((c0 < w + POOL && c1 > w) || (o0 < w + POOL && o1 > w))) {
-          SplitEmitter emit{sh.pool, c0, o0, w, (u32)POOL, (u32)tid << 16};
-          enumerate_split(tile_parent(sh, tid), tb, sh.guard[tid], emit);
-        }
-      } else if (cnt && off < w + POOL && off + cnt > w) {
-        u32 j = off;
-        /* the parent is re-read from shared memory so that it does not occupy registers during phase B */
-        generate_moves(tile_parent(sh, tid), tb, [&](int from, int to, int promo, int kind) {
-          const u32 slot = j++ - w; /* wraps to a huge value below the window */
-          if (slot < (u32)POOL) sh.pool[slot] = ((u32)kind << 28) | ((u32)tid << 16) | pack_move(from, to, promo);
-        });
+    if (LEAF) {
+      /* The pool is filled once per CHUNK of parents: the largest power-of-two fraction of the tile whose
+       * children fit, so that every parent enumerates its moves exactly once.  Inside a chunk the clean
+       * children come first, the others follow. */
+      static_assert(!LEAF || (PARENTS & (PARENTS - 1)) == 0, "K2 halves its tiles");
+      if (tid < PARENTS) sh.offs[tid] = off;
+      if (tid == 0) {
+        const u32 packed_total = (total - clean_total) << 16 | clean_total;
+        sh.offs[PARENTS] = packed_total;
       }
       group_sync<SYNC>(group);
-      const u32 end = min(total - w, (u32)POOL);
-      for (u32 c = tid; c < end; c += GT) {
-        const u32 e = sh.pool[c];
-        if (MODE == TILE_MOVES) {
-          out.moves[out_base + w + c] = (u16)e;
-          continue;
+      if (tid == 0) {
+        u32 chunk = PARENTS;
+        for (; chunk > 1; chunk >>= 1) {
+          bool fits = true;
+          for (u32 a = 0; a < (u32)PARENTS && fits; a += chunk) {
+            const u32 lo = sh.offs[a], hi = sh.offs[a + chunk];
+            fits = ((hi & 0xFFFF) - (lo & 0xFFFF)) + ((hi >> 16) - (lo >> 16)) <= (u32)POOL;
+          }
+          if (fits) break;
         }
-        const int parent = (e >> 16) & 0xFFF;
-        Pos q = tile_parent(sh, parent);
-        if (LEAF) {
+        sh.chunk = chunk;
+      }
+      group_sync<SYNC>(group);
+      const u32 chunk = sh.chunk;
+      for (u32 a = 0; a < (u32)PARENTS; a += chunk) {
+        const u32 lo = sh.offs[a], hi = sh.offs[a + chunk];
+        const u32 clean_base = lo & 0xFFFF, other_base = lo >> 16;
+        const u32 clean_here = (hi & 0xFFFF) - clean_base, end = clean_here + (hi >> 16) - other_base;
+        if (end == 0) continue;
+        if (cnt && (u32)tid >= a && (u32)tid < a + chunk) {
+          /* the parent is re-read from shared memory so that it does not occupy registers during phase B */
+          SplitEmitter emit{sh.pool, (off & 0xFFFF) - clean_base, clean_here + (off >> 16) - other_base, 0, (u32)POOL, (u32)tid << 16};
+          enumerate_split(tile_parent(sh, tid), tb, sh.guard[tid], emit);
+        }
+        group_sync<SYNC>(group);
+        for (u32 c = tid; c < end; c += GT) {
+          const u32 e = sh.pool[c];
+          const int parent = (e >> 16) & 0xFFF;
+          Pos q = tile_parent(sh, parent);
           u32 k;
-          if (w + c < clean_total) { /* quiet move off every line that matters: replies = base + pawns + king */
+          if (c < clean_here) { /* quiet move off every line that matters: replies = base + pawns + king */
             k = count_child_fast(q, tb, (int)(e & 63), (int)((e >> 6) & 63), (int)(e >> 28));
           } else {
             make_move_kind<1, true>(q, tb, (u16)(e & 0xFFFF), (int)(e >> 28));
@@ -900,15 +915,36 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
           }
           if (MULTI_ROOT) atomicAdd(&sh.parent_nodes[parent], k);
           else acc += ACC == WEIGHTED ? k * in.mult[first + tile * PARENTS + parent] : (u64)k;
-        } else {
+        }
+        group_sync<SYNC>(group);
+      }
+    } else {
+      for (u32 w = 0; w < total; w += POOL) { /* sliding windows over the tile's children */
+        if (cnt && off < w + POOL && off + cnt > w) {
+          u32 j = off;
+          generate_moves(tile_parent(sh, tid), tb, [&](int from, int to, int promo, int kind) {
+            const u32 slot = j++ - w; /* wraps to a huge value below the window */
+            if (slot < (u32)POOL) sh.pool[slot] = ((u32)kind << 28) | ((u32)tid << 16) | pack_move(from, to, promo);
+          });
+        }
+        group_sync<SYNC>(group);
+        const u32 end = min(total - w, (u32)POOL);
+        for (u32 c = tid; c < end; c += GT) {
+          const u32 e = sh.pool[c];
+          if (MODE == TILE_MOVES) {
+            out.moves[out_base + w + c] = (u16)e;
+            continue;
+          }
+          const int parent = (e >> 16) & 0xFFF;
+          Pos q = tile_parent(sh, parent);
           make_move(q, tb, (u16)(e & 0xFFFF));
           const size_t o = (size_t)(out_base + w + c);
           store_pos(out.children.rec, out.children.stride, o, q);
           if (MULTI_ROOT) out.children.roots[o] = in.roots[first + tile * PARENTS + parent];
           if (ACC == WEIGHTED) out.children.mult[o] = in.mult[first + tile * PARENTS + parent];
         }
+        group_sync<SYNC>(group);
       }
-      group_sync<SYNC>(group);
     }
     if (LEAF && MULTI_ROOT) {
       if (valid && sh.parent_nodes[tid]) atomicAdd(out.nodes + in.roots[first + i], (unsigned long long)sh.parent_nodes[tid]);
