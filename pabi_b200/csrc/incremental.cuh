@@ -29,20 +29,15 @@ constexpr int META_BASE = 32;
 
 struct TContext {
   u64 reach; /* union of T's slider attack sets: a clean move neither leaves nor lands on it; ~0 = no clean moves */
+  u64 guard; /* reach plus the king guard below: a clean move does not leave it, a clean slider move does not land on it */
   u32 base;  /* moves of T's knights, bishops, rooks and queens in the parent position */
 };
 
-/* The squares on the rays from T's king up to and including the SECOND piece of each ray.  Only there
- * can a move change who checks or pins: a piece leaving (it is the first or second blocker of the ray)
- * or a slider arriving (it sees the king, or pins the single blocker).  Farther out at least two pieces
- * shield the king whatever happens to a third, and a knight or pawn arriving on a ray changes nothing. */
-template <class TB>
-PB_HD u64 king_guard(const Pos& n, const TB& tb, int tk) {
-  const u64 occ = n.pawns | n.knights | n.bishops | n.rooks | n.queens | n.kings;
-  const u64 kd = tb.bishop(tk, occ), ko = tb.rook(tk, occ);
-  return tb.bishop(tk, occ & ~kd) | tb.rook(tk, occ & ~ko);
-}
-
+/* King guard: the squares on the rays from T's king up to and including the SECOND piece of each ray.
+ * Only there can a move change who checks or pins: a piece leaving (it is the first or second blocker of
+ * the ray) or a slider arriving (it sees the king, or pins the single blocker).  Farther out at least two
+ * pieces shield the king whatever happens to a third, and a knight or pawn arriving on a ray changes
+ * nothing. */
 template <class TB>
 PB_HD TContext t_context(const Pos& n, const TB& tb) {
   const u64 occ = n.pawns | n.knights | n.bishops | n.rooks | n.queens | n.kings;
@@ -50,7 +45,7 @@ PB_HD TContext t_context(const Pos& n, const TB& tb) {
   const int tk = lsb(n.kings & W);
   const u64 s_diag = (n.bishops | n.queens) & B, s_orth = (n.rooks | n.queens) & B;
   const u64 kd = tb.bishop(tk, occ), ko = tb.rook(tk, occ);
-  TContext c{~0ULL, 0};
+  TContext c{~0ULL, ~0ULL, 0};
   /* T in check (cannot happen when S is to move in a legal position) or T pieces pinned: no fast path */
   if ((tb.knight(tk) & n.knights & B) | (pawn_attacks(n.kings & W, 0) & n.pawns & B) | (kd & s_diag) | (ko & s_orth)) return c;
   {
@@ -76,6 +71,7 @@ PB_HD TContext t_context(const Pos& n, const TB& tb) {
     base += popc(a & not_w);
   }
   c.reach = reach;
+  c.guard = reach | tb.bishop(tk, occ & ~kd) | tb.rook(tk, occ & ~ko);
   c.base = base;
   return c;
 }
@@ -88,7 +84,7 @@ PB_HD TContext t_context(const Pos& n, const TB& tb) {
  *   castle(from, to)
  * The union of everything reported is exactly generate_moves(n). */
 template <class TB, class Sink>
-PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 reach, Sink& sink) {
+PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 reach, u64 guard, Sink& sink) {
   Analysis a;
   analyze<1>(n, tb, a);
   sink.piece(a.king, KIND_KING, 0, a.safe_king);
@@ -98,7 +94,6 @@ PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 reach, Sink& sink) {
   const u64 tk_bb = n.kings & W;
   const int tk = lsb(tk_bb);
   /* a clean move leaves a square outside `guard`; a slider lands outside `guard`, a knight or pawn outside `reach` */
-  const u64 guard = reach == ~0ULL ? reach : reach | king_guard(n, tb, tk);
   const u64 open = ~guard & ~W;
   const u64 open_leaper = ~reach & ~W;
 

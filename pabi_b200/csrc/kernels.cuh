@@ -718,7 +718,8 @@ struct TileGroupShared {
   u32 parent_nodes[CFG::PARENTS]; /* K2, multi-root: nodes below each parent */
   u32 warp_sums[CFG::GROUP_THREADS / 32 + 1];
   unsigned long long next_tile; /* TILE_LEAF: the tile this group took from the ticket counter */
-  u64 guard[CFG::PARENTS];      /* TILE_LEAF: TContext::reach of each parent (incremental.cuh) */
+  u64 guard[CFG::PARENTS];      /* TILE_LEAF: TContext::guard of each parent (incremental.cuh) */
+  u64 reach[CFG::PARENTS];      /* TILE_LEAF: TContext::reach */
   u32 offs[CFG::PARENTS + 1];   /* TILE_LEAF: packed exclusive prefix (other << 16 | clean) of the parents' move counts */
   u32 chunk;                    /* TILE_LEAF: parents per pool filling */
 };
@@ -754,13 +755,12 @@ struct TileOut {
 };
 
 /* enumerate_split sink of K2's phase A: clean moves go to pool[clean_at ...), the others to
- * pool[other_at ...); `lo` is the start of the current pool window (slots below it wrap to huge values) */
+ * pool[other_at ...); the chunk was sized so that everything fits */
 struct SplitEmitter {
   u32* pool;
-  u32 clean_at, other_at, lo, cap, tag; /* tag = parent << 16 */
+  u32 clean_at, other_at, tag; /* tag = parent << 16 */
   __device__ __forceinline__ void put(u32& at, int from, int to, int promo, int kind) {
-    const u32 slot = at++ - lo;
-    if (slot < cap) pool[slot] = ((u32)kind << 28) | tag | pack_move(from, to, promo);
+    pool[at++] = ((u32)kind << 28) | tag | pack_move(from, to, promo);
   }
   __device__ __forceinline__ void other(int from, int to, int kind) {
     if (kind == KIND_PAWN && to < 8) { /* black promotes on rank 1 */
@@ -833,9 +833,9 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         if (meta_stm(p.meta) == 0) p = mirror(p);
         const TContext ctx = t_context(p, tb);
         p.meta = (with_king_squares(p) & ~(0xFFFFULL << META_BASE)) | ((u64)ctx.base << META_BASE);
-        sh.guard[tid] = ctx.reach;
+        sh.guard[tid] = ctx.guard, sh.reach[tid] = ctx.reach;
         SplitCounter counter;
-        enumerate_split(p, tb, ctx.reach, counter);
+        enumerate_split(p, tb, ctx.reach, ctx.guard, counter);
         cnt = counter.other << 16 | counter.clean;
       }
       sh.parents[0][tid] = p.white, sh.parents[1][tid] = p.pawns, sh.parents[2][tid] = p.knights;
@@ -898,8 +898,8 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         if (end == 0) continue;
         if (cnt && (u32)tid >= a && (u32)tid < a + chunk) {
           /* the parent is re-read from shared memory so that it does not occupy registers during phase B */
-          SplitEmitter emit{sh.pool, (off & 0xFFFF) - clean_base, clean_here + (off >> 16) - other_base, 0, (u32)POOL, (u32)tid << 16};
-          enumerate_split(tile_parent(sh, tid), tb, sh.guard[tid], emit);
+          SplitEmitter emit{sh.pool, (off & 0xFFFF) - clean_base, clean_here + (off >> 16) - other_base, (u32)tid << 16};
+          enumerate_split(tile_parent(sh, tid), tb, sh.reach[tid], sh.guard[tid], emit);
         }
         group_sync<SYNC>(group);
         for (u32 c = tid; c < end; c += GT) {

@@ -210,9 +210,9 @@ static void incremental_walk(const Pos& p, const Tables& tb, int depth, uint64_t
   const TContext ctx = t_context(n, tb);
   n.meta = (with_king_squares(n) & ~(0xFFFFULL << META_BASE)) | ((u64)ctx.base << META_BASE);
   CheckSink sink{n, tb, out};
-  enumerate_split(n, tb, ctx.reach, sink);
+  enumerate_split(n, tb, ctx.reach, ctx.guard, sink);
   SplitCounter counter;
-  enumerate_split(n, tb, ctx.reach, counter);
+  enumerate_split(n, tb, ctx.reach, ctx.guard, counter);
   ++out[0], out[1] += sink.k, out[2] += sink.clean;
   if (counter.clean != sink.clean || counter.other != sink.other) ++out[3];
   /* the split covers exactly the legal moves */
