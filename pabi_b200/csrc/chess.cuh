@@ -246,7 +246,8 @@ struct Analysis {
   u64 safe_king;  /* AttackInfo::safe_king_squares */
   u64 checkers;   /* AttackInfo::checkers */
   u64 pins;       /* AttackInfo::pins */
-  u64 attacks;    /* AttackInfo::attacks, sliders seen through our king (see below) */
+  u64 attacks;    /* AttackInfo::attacks restricted to what move generation reads: exact on the king's
+                     neighbour squares and on the castling walks, sliders seen through our king (see below) */
   u64 block;      /* blocking_ray of position.rs:333-353; 0 when doubly checked */
   int us, king;
 };
@@ -275,29 +276,47 @@ PB_HD void analyze(const Pos& p, const TB& tb, Analysis& a) {
   const u64 their_diag = (p.bishops | p.queens) & their;
   const u64 their_orth = (p.rooks | p.queens) & their;
 
-  u64 att = tb.king(lsb(p.kings & their));
-  att |= pawn_attacks(p.pawns & their, them);
-  for (u64 b = p.knights & their; b; b &= b - 1) att |= tb.knight(lsb(b));
-  for (u64 b = their_diag; b; b &= b - 1) att |= tb.bishop(lsb(b), occ_nk);
-  for (u64 b = their_orth; b; b &= b - 1) att |= tb.rook(lsb(b), occ_nk);
-
   const u64 king_diag = tb.bishop(king, occ);
   const u64 king_orth = tb.rook(king, occ);
   u64 checkers = (tb.knight(king) & p.knights & their) |
                  (pawn_attacks(king_bb, us) & p.pawns & their) | (king_diag & their_diag) |
                  (king_orth & their_orth);
 
+  /* The enemy attack map is only ever read on the squares the king could step to and on the castling
+   * walks (generate_king_moves / generate_castle_moves): it is built from the enemy pieces that can reach
+   * those squares, found with the per-king-square zone tables (see count_moves_white). */
+  const u64 king_targets = tb.king(king) & ~our;
+  u64 need = king_targets;
+  if (checkers == 0) {
+    const int rights = meta_castling(p.meta) >> (2 * us), sh = 56 * us;
+    if ((rights & 1) && (occ & (0x60ULL << sh)) == 0) need |= 0x60ULL << sh;
+    if ((rights & 2) && (occ & (0x0EULL << sh)) == 0) need |= 0x0CULL << sh;
+  }
+  u64 att = 0;
+  if (need) {
+    att = tb.king(lsb(p.kings & their)) | pawn_attacks(p.pawns & their, them);
+    for (Squares b(p.knights & their & tb.s->knight_zone[king]); b.any();) att |= tb.knight(b.pop());
+    for (Squares b(their_diag & tb.s->diag_zone[king]); b.any();) {
+      const int sq = b.pop();
+      if ((tb.s->diag[sq] | tb.s->anti[sq]) & need) att |= tb.bishop(sq, occ_nk);
+    }
+    for (Squares b(their_orth & tb.s->orth_zone[king]); b.any();) {
+      const int sq = b.pop();
+      if (tb.s->orth[sq] & need) att |= tb.rook(sq, occ_nk);
+    }
+  }
+
   u64 pins = 0;
-  {
+  { /* the x-ray lookup only when an enemy slider stands on one of the king's lines behind our piece */
     const u64 cand = king_diag & our;
-    if (cand) {
+    if (cand && ((tb.s->diag[king] | tb.s->anti[king]) & their_diag & ~king_diag)) {
       u64 pinners = tb.bishop(king, occ ^ cand) & ~king_diag & their_diag;
       for (; pinners; pinners &= pinners - 1) pins |= tb.ray(lsb(pinners), king) & cand;
     }
   }
   {
     const u64 cand = king_orth & our;
-    if (cand) {
+    if (cand && (tb.s->orth[king] & their_orth & ~king_orth)) {
       u64 pinners = tb.rook(king, occ ^ cand) & ~king_orth & their_orth;
       for (; pinners; pinners &= pinners - 1) pins |= tb.ray(lsb(pinners), king) & cand;
     }

@@ -154,8 +154,8 @@ static HostTables* build() {
     std::fprintf(stderr, "pabi_b200: slider table sizes %u/%u differ from generated.rs:30,44\n", boff, roff);
     std::abort();
   }
-  for (int k = 0; k < 64; k++) { /* zones: the king's neighbours, plus the castling walk for a king on e1 */
-    const u64 zone = s.king[k] | (k == 4 ? 0x6CULL : 0);
+  for (int k = 0; k < 64; k++) { /* zones: the king's neighbours, plus the castling walk for a king on e1 / e8 */
+    const u64 zone = s.king[k] | (k == 4 ? 0x6CULL : k == 60 ? 0x6CULL << 56 : 0);
     for (u64 z = zone; z; z &= z - 1) {
       const int t = lsb(z);
       s.knight_zone[k] |= s.knight[t];
