@@ -46,32 +46,46 @@ PB_HD TContext t_context(const Pos& n, const TB& tb) {
   const u64 s_diag = (n.bishops | n.queens) & B, s_orth = (n.rooks | n.queens) & B;
   const u64 kd = tb.bishop(tk, occ), ko = tb.rook(tk, occ);
   TContext c{~0ULL, ~0ULL, 0};
-  /* T in check (cannot happen when S is to move in a legal position) or T pieces pinned: no fast path */
+  /* T in check (cannot happen when S is to move in a legal position): no fast path */
   if ((tb.knight(tk) & n.knights & B) | (pawn_attacks(n.kings & W, 0) & n.pawns & B) | (kd & s_diag) | (ko & s_orth)) return c;
+  /* T's pinned pieces: their restricted mobility goes into `base` (a clean move leaves the pins as they
+   * are); a pinned T pawn would need the pin-aware pawn count, so such parents take the full path */
+  u64 pins = 0;
   {
     const u64 cand = kd & W;
-    if (cand && (tb.bishop(tk, occ ^ cand) & ~kd & s_diag)) return c;
+    if (cand) {
+      u64 pinners = tb.bishop(tk, occ ^ cand) & ~kd & s_diag;
+      for (; pinners; pinners &= pinners - 1) pins |= tb.ray(lsb(pinners), tk) & cand;
+    }
   }
   {
     const u64 cand = ko & W;
-    if (cand && (tb.rook(tk, occ ^ cand) & ~ko & s_orth)) return c;
+    if (cand) {
+      u64 pinners = tb.rook(tk, occ ^ cand) & ~ko & s_orth;
+      for (; pinners; pinners &= pinners - 1) pins |= tb.ray(lsb(pinners), tk) & cand;
+    }
   }
+  if (pins & n.pawns) return c;
   const u64 not_w = ~W;
   u64 reach = 0;
   u32 base = 0;
-  for (Squares b(n.knights & W); b.any();) base += popc(tb.knight(b.pop()) & not_w);
+  for (Squares b(n.knights & W & ~pins); b.any();) base += popc(tb.knight(b.pop()) & not_w);
   for (Squares b((n.rooks | n.queens) & W); b.any();) {
-    const u64 a = tb.rook(b.pop(), occ);
+    const int sq = b.pop();
+    const u64 a = tb.rook(sq, occ);
     reach |= a;
-    base += popc(a & not_w);
+    base += popc(a & not_w & ((pins >> sq) & 1 ? tb.line(tk, sq) : ~0ULL));
   }
   for (Squares b((n.bishops | n.queens) & W); b.any();) {
-    const u64 a = tb.bishop(b.pop(), occ);
+    const int sq = b.pop();
+    const u64 a = tb.bishop(sq, occ);
     reach |= a;
-    base += popc(a & not_w);
+    base += popc(a & not_w & ((pins >> sq) & 1 ? tb.line(tk, sq) : ~0ULL));
   }
-  c.reach = reach;
   c.guard = reach | tb.bishop(tk, occ & ~kd) | tb.rook(tk, occ & ~ko);
+  /* with a T piece pinned, a knight, pawn or king arriving between it and its pinner would free it:
+   * such parents hold every mover to the full guard */
+  c.reach = pins ? c.guard : reach;
   c.base = base;
   return c;
 }
@@ -87,15 +101,19 @@ template <class TB, class Sink>
 PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 reach, u64 guard, Sink& sink) {
   Analysis a;
   analyze<1>(n, tb, a);
-  sink.piece(a.king, KIND_KING, 0, a.safe_king);
-  if (a.block == 0) return;
-  const u64 targets = ~a.our & a.block;
   const u64 W = a.their;
   const u64 tk_bb = n.kings & W;
   const int tk = lsb(tk_bb);
-  /* a clean move leaves a square outside `guard`; a slider lands outside `guard`, a knight or pawn outside `reach` */
+  /* a clean move leaves a square outside `guard`; a slider lands outside `guard`; a knight, pawn or king
+   * outside `reach` (arriving on a king ray they change neither checks nor pins) */
   const u64 open = ~guard & ~W;
   const u64 open_leaper = ~reach & ~W;
+  {
+    const u64 c = (guard >> a.king) & 1 ? 0 : a.safe_king & open_leaper;
+    sink.piece(a.king, KIND_KING, c, a.safe_king & ~c);
+  }
+  if (a.block == 0) return;
+  const u64 targets = ~a.our & a.block;
 
   for (Squares b(n.knights & a.our & ~a.pins); b.any();) {
     const int from = b.pop();
@@ -188,20 +206,22 @@ PB_HD u32 king_part_white(u64 our, u64 their, u64 occ, u64 pawns, u64 knights, u
 }
 
 /* Replies to a clean move: n = the normalised parent (black to move; meta carries base and both king
- * squares), the move is quiet, by a pawn, knight, bishop, rook or queen. */
+ * squares), the move is quiet and not a castling move. */
 template <class TB>
 PB_HD u32 count_child_fast(const Pos& n, const TB& tb, int from, int to, int kind) {
   const u64 m = bit(from) | bit(to);
-  u64 pawns = n.pawns, knights = n.knights, bishops = n.bishops, rooks = n.rooks, queens = n.queens;
+  u64 pawns = n.pawns, knights = n.knights, bishops = n.bishops, rooks = n.rooks, queens = n.queens, kings = n.kings;
+  const int king = (int)(n.meta >> META_OTHER_KING) & 63;
+  int their_king = (int)(n.meta >> META_MOVER_KING) & 63;
   if (kind == KIND_PAWN) pawns ^= m;
   else if (kind == KIND_KNIGHT) knights ^= m;
   else if (kind == KIND_BISHOP) bishops ^= m;
   else if (kind == KIND_ROOK) rooks ^= m;
-  else queens ^= m;
+  else if (kind == KIND_QUEEN) queens ^= m;
+  else kings ^= m, their_king = to; /* a plain king step (castling is never clean) */
   const u64 W = n.white;
-  const u64 occ = pawns | knights | bishops | rooks | queens | n.kings;
+  const u64 occ = pawns | knights | bishops | rooks | queens | kings;
   const u64 their = occ ^ W;
-  const int king = (int)(n.meta >> META_OTHER_KING) & 63, their_king = (int)(n.meta >> META_MOVER_KING) & 63;
   u32 cnt = (u32)(n.meta >> META_BASE) & 0xFFFF;
   cnt += king_part_white(W, their, occ, pawns, knights, bishops | queens, rooks | queens, meta_castling(n.meta) & 3, king, their_king, tb);
   /* T's pawns: nothing pinned, no check, no en passant square (position.rs:1106-1224 set-wise) */
