@@ -81,6 +81,7 @@ struct Squares {
 constexpr u64 FILE_A = 0x0101010101010101ULL;
 constexpr u64 FILE_H = 0x8080808080808080ULL;
 constexpr u64 RANK_1 = 0x00000000000000FFULL;
+constexpr u64 RANK_2 = 0x000000000000FF00ULL;
 constexpr u64 RANK_3 = 0x0000000000FF0000ULL;
 constexpr u64 RANK_6 = 0x0000FF0000000000ULL;
 constexpr u64 RANK_8 = 0xFF00000000000000ULL;

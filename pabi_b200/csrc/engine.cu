@@ -163,11 +163,11 @@ constexpr size_t FLAT_SMEM = sizeof(SharedTables);
  * choice can be re-measured on the device (environment variable PABI_TILE_VARIANT). */
 /* 1024 threads (64 registers each, 32 warps per SM) in four independent 256-thread groups that share one
  * table image: while one group scans / generates, the others count */
-using TileDefault = TileConfig<1024, 256, 5632, 1, 4>;
+using TileDefault = TileConfig<1024, 256, 5120, 1, 4>;
 using TileV1 = TileConfig<1024, 512, 8192, 1, 2>;
 using TileV2 = TileConfig<1024, 1024, 16384, 1, 1>;
-using TileV3 = TileConfig<1024, 256, 5120, 1, 4>;
-using TileV4 = TileConfig<1024, 128, 2816, 1, 8>;
+using TileV3 = TileConfig<1024, 256, 4608, 1, 4>;
+using TileV4 = TileConfig<1024, 128, 2560, 1, 8>;
 using TileV5 = TileConfig<768, 256, 6144, 1, 3>;
 constexpr int TILE_VARIANTS = 6;
 
@@ -201,6 +201,7 @@ template <TileMode MODE, Accounting ACC, class CFG>
 void launch_tile_cfg(pabi_cuda_ctx* ctx, Frontier in, size_t first, size_t n, const u64* prefix, TileOut out) {
   static bool configured[8] = {};
   if (!configured[ctx->device & 7]) { /* the table image alone exceeds the default 48 KB of dynamic shared memory */
+    static_assert(sizeof(TileShared<CFG>) <= 232448, "a tile geometry must fit the 227 KB of shared memory a block may use");
     CK(cudaFuncSetAttribute(k_tile<MODE, ACC, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared<CFG>)));
     configured[ctx->device & 7] = true;
   }

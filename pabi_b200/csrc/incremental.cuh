@@ -30,8 +30,60 @@ constexpr int META_BASE = 32;
 struct TContext {
   u64 reach; /* union of T's slider attack sets: a clean move neither leaves nor lands on it; ~0 = no clean moves */
   u64 guard; /* reach plus the king guard below: a clean move does not leave it, a clean slider move does not land on it */
+  u64 zone;  /* squares T's pawn and king moves depend on: a clean move that also stays off it is INERT */
   u32 base;  /* moves of T's knights, bishops, rooks and queens in the parent position */
+  u32 total; /* base + T's pawn and king moves in the parent position = the reply count of every inert move */
 };
+
+/* king steps + castling of a white-to-move position that is not in check (the `need` / `rem` scan of
+ * count_moves_white) */
+template <class TB>
+PB_HD u32 king_part_white(u64 our, u64 their, u64 occ, u64 pawns, u64 knights, u64 diag_sliders, u64 orth_sliders, int rights, int king,
+                          int their_king, const TB& tb) {
+  const u64 king_targets = tb.king(king) & ~our;
+  u64 castle_walks = 0;
+  if (rights) {
+    if ((rights & 1) && (occ & 0x60ULL) == 0) castle_walks = 0x60ULL;
+    if ((rights & 2) && (occ & 0x0EULL) == 0) castle_walks |= 0x0CULL;
+  }
+  const u64 need = king_targets | castle_walks;
+  if (!need) return 0;
+  const u64 occ_nk = occ ^ bit(king);
+  u64 rem = need & ~(tb.king(their_king) | pawn_attacks(pawns & their, 1));
+  for (Squares b(knights & their & tb.s->knight_zone[king]); b.any();) rem &= ~tb.knight(b.pop());
+  for (Squares b(diag_sliders & their & tb.s->diag_zone[king]); b.any() && rem;) {
+    const int sq = b.pop();
+    if ((tb.s->diag[sq] | tb.s->anti[sq]) & rem) rem &= ~tb.bishop(sq, occ_nk);
+  }
+  for (Squares b(orth_sliders & their & tb.s->orth_zone[king]); b.any() && rem;) {
+    const int sq = b.pop();
+    if (tb.s->orth[sq] & rem) rem &= ~tb.rook(sq, occ_nk);
+  }
+  u32 n = popc(king_targets & rem);
+  if (castle_walks) {
+    const u64 safe_walks = castle_walks & rem;
+    n += ((safe_walks & 0x60ULL) == 0x60ULL) + ((safe_walks & 0x0CULL) == 0x0CULL);
+  }
+  return n;
+}
+
+/* T's pawn moves when nothing is pinned, T is not in check and there is no en passant square
+ * (position.rs:1106-1224 set-wise), plus T's king moves */
+template <class TB>
+PB_HD u32 pawn_king_part_white(u64 W, u64 pawns, u64 knights, u64 bishops, u64 rooks, u64 queens, u64 kings, int rights, int king,
+                               int their_king, const TB& tb) {
+  const u64 occ = pawns | knights | bishops | rooks | queens | kings;
+  const u64 their = occ ^ W;
+  u32 cnt = king_part_white(W, their, occ, pawns, knights, bishops | queens, rooks | queens, rights, king, their_king, tb);
+  const u64 wp = pawns & W;
+  const u64 west = ((wp & ~FILE_A) << 7) & their;
+  const u64 east = ((wp & ~FILE_H) << 9) & their;
+  const u64 single = (wp << 8) & ~occ;
+  const u64 dbl = ((single & RANK_3) << 8) & ~occ;
+  cnt += popc(west) + popc(east) + popc(single) + popc(dbl);
+  if ((west | east | single) & RANK_8) cnt += 3 * (popc(west & RANK_8) + popc(east & RANK_8) + popc(single & RANK_8));
+  return cnt;
+}
 
 /* King guard: the squares on the rays from T's king up to and including the SECOND piece of each ray.
  * Only there can a move change who checks or pins: a piece leaving (it is the first or second blocker of
@@ -45,7 +97,7 @@ PB_HD TContext t_context(const Pos& n, const TB& tb) {
   const int tk = lsb(n.kings & W);
   const u64 s_diag = (n.bishops | n.queens) & B, s_orth = (n.rooks | n.queens) & B;
   const u64 kd = tb.bishop(tk, occ), ko = tb.rook(tk, occ);
-  TContext c{~0ULL, ~0ULL, 0};
+  TContext c{~0ULL, ~0ULL, ~0ULL, 0, 0};
   /* T in check (cannot happen when S is to move in a legal position): no fast path */
   if ((tb.knight(tk) & n.knights & B) | (pawn_attacks(n.kings & W, 0) & n.pawns & B) | (kd & s_diag) | (ko & s_orth)) return c;
   /* T's pinned pieces: their restricted mobility goes into `base` (a clean move leaves the pins as they
@@ -87,6 +139,25 @@ PB_HD TContext t_context(const Pos& n, const TB& tb) {
    * such parents hold every mover to the full guard */
   c.reach = pins ? c.guard : reach;
   c.base = base;
+  /* Inert moves.  T's pawn moves depend on the squares in front of and diagonally ahead of its pawns; its king
+   * moves on the king's neighbourhood (and the castling walks) and on every square from which a piece can see
+   * one of those squares.  An S move that is clean and whose two squares lie outside this zone leaves the
+   * visible set of every such square unchanged, so T has exactly the moves it would have had in the parent
+   * position with the move passed: `total`. */
+  const u64 wp = n.pawns & W;
+  const int rights = meta_castling(n.meta) & 3;
+  u64 zone = (wp << 8) | ((wp & RANK_2) << 16) | ((wp & ~FILE_A) << 7) | ((wp & ~FILE_H) << 9);
+  u64 watched = tb.king(tk) & not_w; /* squares whose attackers matter */
+  if (rights & 1) zone |= 0x60ULL, watched |= (occ & 0x60ULL) ? 0 : 0x60ULL;
+  if (rights & 2) zone |= 0x0EULL, watched |= (occ & 0x0EULL) ? 0 : 0x0CULL;
+  zone |= watched;
+  const u64 occ_nk = occ ^ (n.kings & W);
+  for (Squares b(watched); b.any();) {
+    const int sq = b.pop();
+    zone |= tb.bishop(sq, occ_nk) | tb.rook(sq, occ_nk) | tb.knight(sq);
+  }
+  c.zone = zone;
+  c.total = base + pawn_king_part_white(W, n.pawns, n.knights, n.bishops, n.rooks, n.queens, n.kings, rights, tk, lsb(n.kings & B), tb);
   return c;
 }
 
@@ -163,47 +234,26 @@ PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 reach, u64 guard, Sin
   if (c & 2) sink.castle(60, 58);
 }
 
-/* (clean, other) move counts of a parent: the sizing pass of the split pool */
+/* (clean, other, inert) move counts of a parent: the sizing pass of the split pool.  Inert moves (clean and
+ * off the parent's zone) are never materialised: each of them has TContext::total replies. */
+PB_HD u64 inert_targets(u64 zone, int from, u64 clean) { return (zone >> from) & 1 ? 0 : clean & ~zone; }
+PB_HD u64 inert_pushes(u64 zone, u64 clean, int delta) { return clean & ~zone & ~(zone >> delta); } /* from = to + delta */
+
 struct SplitCounter {
-  u32 clean = 0, other = 0;
-  PB_HD void piece(int, int, u64 c, u64 o) { clean += popc(c), other += popc(o); }
-  PB_HD void pushes(u64 c, u64 o, int) { clean += popc(c), other += popc(o) + 3 * popc(o & RANK_1); }
+  u64 zone;
+  u32 clean = 0, other = 0, inert = 0;
+  PB_HD void piece(int from, int, u64 c, u64 o) {
+    const u32 i = popc(inert_targets(zone, from, c));
+    inert += i, clean += popc(c) - i, other += popc(o);
+  }
+  PB_HD void pushes(u64 c, u64 o, int delta) {
+    const u32 i = popc(inert_pushes(zone, c, delta));
+    inert += i, clean += popc(c) - i, other += popc(o) + 3 * popc(o & RANK_1);
+  }
   PB_HD void pawn_capture(int, int to) { other += to < 8 ? 4 : 1; }
   PB_HD void en_passant(int, int) { ++other; }
   PB_HD void castle(int, int) { ++other; }
 };
-
-/* king steps + castling of a white-to-move position that is not in check (the `need` / `rem` scan of
- * count_moves_white) */
-template <class TB>
-PB_HD u32 king_part_white(u64 our, u64 their, u64 occ, u64 pawns, u64 knights, u64 diag_sliders, u64 orth_sliders, int rights, int king,
-                          int their_king, const TB& tb) {
-  const u64 king_targets = tb.king(king) & ~our;
-  u64 castle_walks = 0;
-  if (rights) {
-    if ((rights & 1) && (occ & 0x60ULL) == 0) castle_walks = 0x60ULL;
-    if ((rights & 2) && (occ & 0x0EULL) == 0) castle_walks |= 0x0CULL;
-  }
-  const u64 need = king_targets | castle_walks;
-  if (!need) return 0;
-  const u64 occ_nk = occ ^ bit(king);
-  u64 rem = need & ~(tb.king(their_king) | pawn_attacks(pawns & their, 1));
-  for (Squares b(knights & their & tb.s->knight_zone[king]); b.any();) rem &= ~tb.knight(b.pop());
-  for (Squares b(diag_sliders & their & tb.s->diag_zone[king]); b.any() && rem;) {
-    const int sq = b.pop();
-    if ((tb.s->diag[sq] | tb.s->anti[sq]) & rem) rem &= ~tb.bishop(sq, occ_nk);
-  }
-  for (Squares b(orth_sliders & their & tb.s->orth_zone[king]); b.any() && rem;) {
-    const int sq = b.pop();
-    if (tb.s->orth[sq] & rem) rem &= ~tb.rook(sq, occ_nk);
-  }
-  u32 n = popc(king_targets & rem);
-  if (castle_walks) {
-    const u64 safe_walks = castle_walks & rem;
-    n += ((safe_walks & 0x60ULL) == 0x60ULL) + ((safe_walks & 0x0CULL) == 0x0CULL);
-  }
-  return n;
-}
 
 /* Replies to a clean move: n = the normalised parent (black to move; meta carries base and both king
  * squares), the move is quiet and not a castling move. */
@@ -219,20 +269,8 @@ PB_HD u32 count_child_fast(const Pos& n, const TB& tb, int from, int to, int kin
   else if (kind == KIND_ROOK) rooks ^= m;
   else if (kind == KIND_QUEEN) queens ^= m;
   else kings ^= m, their_king = to; /* a plain king step (castling is never clean) */
-  const u64 W = n.white;
-  const u64 occ = pawns | knights | bishops | rooks | queens | kings;
-  const u64 their = occ ^ W;
-  u32 cnt = (u32)(n.meta >> META_BASE) & 0xFFFF;
-  cnt += king_part_white(W, their, occ, pawns, knights, bishops | queens, rooks | queens, meta_castling(n.meta) & 3, king, their_king, tb);
-  /* T's pawns: nothing pinned, no check, no en passant square (position.rs:1106-1224 set-wise) */
-  const u64 wp = pawns & W;
-  const u64 west = ((wp & ~FILE_A) << 7) & their;
-  const u64 east = ((wp & ~FILE_H) << 9) & their;
-  const u64 single = (wp << 8) & ~occ;
-  const u64 dbl = ((single & RANK_3) << 8) & ~occ;
-  cnt += popc(west) + popc(east) + popc(single) + popc(dbl);
-  if ((west | east | single) & RANK_8) cnt += 3 * (popc(west & RANK_8) + popc(east & RANK_8) + popc(single & RANK_8));
-  return cnt;
+  return ((u32)(n.meta >> META_BASE) & 0xFFFF) +
+         pawn_king_part_white(n.white, pawns, knights, bishops, rooks, queens, kings, meta_castling(n.meta) & 3, king, their_king, tb);
 }
 
 } /* namespace pabi */

@@ -720,6 +720,7 @@ struct TileGroupShared {
   unsigned long long next_tile; /* TILE_LEAF: the tile this group took from the ticket counter */
   u64 guard[CFG::PARENTS];      /* TILE_LEAF: TContext::guard of each parent (incremental.cuh) */
   u64 reach[CFG::PARENTS];      /* TILE_LEAF: TContext::reach */
+  u64 zone[CFG::PARENTS];       /* TILE_LEAF: TContext::zone */
   u32 offs[CFG::PARENTS + 1];   /* TILE_LEAF: packed exclusive prefix (other << 16 | clean) of the parents' move counts */
   u32 chunk;                    /* TILE_LEAF: parents per pool filling */
 };
@@ -759,6 +760,7 @@ struct TileOut {
 struct SplitEmitter {
   u32* pool;
   u32 clean_at, other_at, tag; /* tag = parent << 16 */
+  u64 zone;                    /* inert moves (incremental.cuh) were accounted for in the sizing pass */
   __device__ __forceinline__ void put(u32& at, int from, int to, int promo, int kind) {
     pool[at++] = ((u32)kind << 28) | tag | pack_move(from, to, promo);
   }
@@ -771,11 +773,11 @@ struct SplitEmitter {
     }
   }
   __device__ __forceinline__ void piece(int from, int kind, u64 c, u64 o) {
-    for (Squares t(c); t.any();) put(clean_at, from, t.pop(), 0, kind);
+    for (Squares t(c & ~inert_targets(zone, from, c)); t.any();) put(clean_at, from, t.pop(), 0, kind);
     for (Squares t(o); t.any();) put(other_at, from, t.pop(), 0, kind);
   }
   __device__ __forceinline__ void pushes(u64 c, u64 o, int delta) {
-    for (Squares t(c); t.any();) {
+    for (Squares t(c & ~inert_pushes(zone, c, delta)); t.any();) {
       const int to = t.pop();
       put(clean_at, to + delta, to, 0, KIND_PAWN);
     }
@@ -807,6 +809,7 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
   const int tid = GROUPS == 1 ? threadIdx.x : threadIdx.x % GT;
   TileGroupShared<CFG>& sh = block.group[group];
   u64 acc = 0;
+  u32 inert_children = 0; /* K2 statistics: children that were never materialised */
   const size_t n_tiles = (n + PARENTS - 1) / PARENTS;
 
   /* K2 takes tiles from a ticket counter (their cost varies, and a static split leaves a tail of idle
@@ -822,6 +825,7 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
     const bool valid = tid < PARENTS && i < n;
     u32 cnt = 0, off = 0, total;
     u32 clean_total = 0; /* K2: the first clean_total children of the tile take the fast path */
+    u32 inert_nodes = 0; /* K2: replies to this parent's inert moves */
     u64 out_base = 0; /* global index of this tile's first child / move */
     if (valid) {
       Pos p = load_pos(in.rec, in.stride, first + i);
@@ -833,17 +837,21 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         if (meta_stm(p.meta) == 0) p = mirror(p);
         const TContext ctx = t_context(p, tb);
         p.meta = (with_king_squares(p) & ~(0xFFFFULL << META_BASE)) | ((u64)ctx.base << META_BASE);
-        sh.guard[tid] = ctx.guard, sh.reach[tid] = ctx.reach;
-        SplitCounter counter;
+        sh.guard[tid] = ctx.guard, sh.reach[tid] = ctx.reach, sh.zone[tid] = ctx.zone;
+        SplitCounter counter{ctx.zone};
         enumerate_split(p, tb, ctx.reach, ctx.guard, counter);
         cnt = counter.other << 16 | counter.clean;
+        /* inert moves are settled here: each has ctx.total replies */
+        inert_children += counter.inert;
+        inert_nodes = counter.inert * ctx.total;
+        if (!MULTI_ROOT) acc += ACC == WEIGHTED ? (u64)inert_nodes * in.mult[first + i] : (u64)inert_nodes;
       }
       sh.parents[0][tid] = p.white, sh.parents[1][tid] = p.pawns, sh.parents[2][tid] = p.knights;
       sh.parents[3][tid] = p.bishops, sh.parents[4][tid] = p.rooks, sh.parents[5][tid] = p.queens;
       sh.parents[6][tid] = p.kings, sh.parents[7][tid] = p.meta;
     }
     if (LEAF) {
-      if (MULTI_ROOT && tid < PARENTS) sh.parent_nodes[tid] = 0;
+      if (MULTI_ROOT && tid < PARENTS) sh.parent_nodes[tid] = inert_nodes;
       off = block_exclusive_scan<GT, SYNC>(cnt, sh.warp_sums, total, tid, group); /* both halves: < 2^16 per tile */
       clean_total = total & 0xFFFF;
       total = clean_total + (total >> 16);
@@ -898,7 +906,7 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         if (end == 0) continue;
         if (cnt && (u32)tid >= a && (u32)tid < a + chunk) {
           /* the parent is re-read from shared memory so that it does not occupy registers during phase B */
-          SplitEmitter emit{sh.pool, (off & 0xFFFF) - clean_base, clean_here + (off >> 16) - other_base, (u32)tid << 16};
+          SplitEmitter emit{sh.pool, (off & 0xFFFF) - clean_base, clean_here + (off >> 16) - other_base, (u32)tid << 16, sh.zone[tid]};
           enumerate_split(tile_parent(sh, tid), tb, sh.reach[tid], sh.guard[tid], emit);
         }
         group_sync<SYNC>(group);
@@ -950,6 +958,11 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
       if (valid && sh.parent_nodes[tid]) atomicAdd(out.nodes + in.roots[first + i], (unsigned long long)sh.parent_nodes[tid]);
       group_sync<SYNC>(group);
     }
+  }
+  if (LEAF) { /* statistics: the inert children were visited too */
+    u32 v = inert_children;
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out.visited, (unsigned long long)v);
   }
   if (LEAF && !MULTI_ROOT) block_add_u64<CFG::THREADS>(acc, block.red, out.nodes);
 }

@@ -155,12 +155,27 @@ uint64_t hostcheck_walk_compare(const pabi_position_t* root, int depth, oracle_g
 
 /* incremental.cuh: for every node of the tree as a parent, every move classified clean must have
  * fast count == full count, the split must cover exactly the generated moves, and the counting sink
- * must agree with what is enumerated.  out[0] parents, out[1] moves, out[2] clean moves, out[3] mismatches. */
+ * must agree with what is enumerated; every inert move (clean and off the parent's zone) must have exactly
+ * TContext::total replies.  out[0] parents, out[1] moves, out[2] clean moves (inert included), out[3] mismatches,
+ * out[4] inert moves. */
 struct CheckSink {
   const Pos& n;
   const Tables& tb;
   uint64_t* out;
-  uint32_t clean = 0, other = 0;
+  const TContext& ctx;
+  uint32_t clean = 0, other = 0, inert = 0;
+  void clean_move(int from, int to, int kind, bool is_inert) {
+    ++clean;
+    moves[k++] = pack_move(from, to, 0);
+    Pos ch = n;
+    make_move_kind<1, true>(ch, tb, pack_move(from, to, 0), kind);
+    const uint32_t want = count_child_white(ch, tb);
+    if (count_child_fast(n, tb, from, to, kind) != want) ++out[3];
+    if (is_inert) {
+      ++inert;
+      if (ctx.total != want) ++out[3];
+    }
+  }
   uint16_t moves[512];
   uint32_t k = 0;
   void full(int from, int to, int promo, int kind) {
@@ -169,32 +184,23 @@ struct CheckSink {
     (void)kind;
   }
   void piece(int from, int kind, u64 c, u64 o) {
+    const u64 in = inert_targets(ctx.zone, from, c);
     for (Squares t(c); t.any();) {
       const int to = t.pop();
-      ++clean;
-      moves[k++] = pack_move(from, to, 0);
-      Pos ch = n;
-      make_move_kind<1, true>(ch, tb, pack_move(from, to, 0), kind);
-      if (count_child_fast(n, tb, from, to, kind) != count_child_white(ch, tb)) ++out[3];
+      clean_move(from, to, kind, (in >> to) & 1);
     }
     for (Squares t(o); t.any();) full(from, t.pop(), 0, kind);
   }
   void pushes(u64 c, u64 o, int delta) {
-    piece_pawn(c, delta);
+    const u64 in = inert_pushes(ctx.zone, c, delta);
+    for (Squares t(c); t.any();) {
+      const int to = t.pop();
+      clean_move(to + delta, to, KIND_PAWN, (in >> to) & 1);
+    }
     for (Squares t(o); t.any();) {
       const int to = t.pop();
       if (to < 8) for (int pr = 4; pr >= 1; pr--) full(to + delta, to, pr, KIND_PAWN);
       else full(to + delta, to, 0, KIND_PAWN);
-    }
-  }
-  void piece_pawn(u64 c, int delta) {
-    for (Squares t(c); t.any();) {
-      const int to = t.pop();
-      ++clean;
-      moves[k++] = pack_move(to + delta, to, 0);
-      Pos ch = n;
-      make_move_kind<1, true>(ch, tb, pack_move(to + delta, to, 0), KIND_PAWN);
-      if (count_child_fast(n, tb, to + delta, to, KIND_PAWN) != count_child_white(ch, tb)) ++out[3];
     }
   }
   void pawn_capture(int from, int to) {
@@ -209,12 +215,12 @@ static void incremental_walk(const Pos& p, const Tables& tb, int depth, uint64_t
   Pos n = meta_stm(p.meta) == 0 ? mirror(p) : p;
   const TContext ctx = t_context(n, tb);
   n.meta = (with_king_squares(n) & ~(0xFFFFULL << META_BASE)) | ((u64)ctx.base << META_BASE);
-  CheckSink sink{n, tb, out};
+  CheckSink sink{n, tb, out, ctx};
   enumerate_split(n, tb, ctx.reach, ctx.guard, sink);
-  SplitCounter counter;
+  SplitCounter counter{ctx.zone};
   enumerate_split(n, tb, ctx.reach, ctx.guard, counter);
-  ++out[0], out[1] += sink.k, out[2] += sink.clean;
-  if (counter.clean != sink.clean || counter.other != sink.other) ++out[3];
+  ++out[0], out[1] += sink.k, out[2] += sink.clean, out[4] += sink.inert;
+  if (counter.clean + counter.inert != sink.clean || counter.other != sink.other || counter.inert != sink.inert) ++out[3];
   /* the split covers exactly the legal moves */
   uint16_t want[256];
   uint32_t nw = 0;
@@ -238,8 +244,8 @@ static void incremental_walk(const Pos& p, const Tables& tb, int depth, uint64_t
   }
 }
 
-void hostcheck_incremental(const pabi_position_t* root, int depth, uint64_t out[4]) {
-  out[0] = out[1] = out[2] = out[3] = 0;
+void hostcheck_incremental(const pabi_position_t* root, int depth, uint64_t out[5]) {
+  out[0] = out[1] = out[2] = out[3] = out[4] = 0;
   incremental_walk(pack_record(*root), host_tb(), depth, out);
 }
 

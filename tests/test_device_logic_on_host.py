@@ -194,7 +194,7 @@ def test_attack_info_matches_the_reference_pictures_and_the_oracle(vectors):
 
 
 def incremental(p, depth):
-    out = (C.c_uint64 * 4)()
+    out = (C.c_uint64 * 5)()
     hostcheck.lib().hostcheck_incremental(C.byref(p), depth, out)
     return tuple(out)
 
@@ -204,8 +204,8 @@ def test_quiet_move_fast_path_is_exact(fen, depth):
     """incremental.cuh: at every node of the tree taken as a K2 parent, (1) the clean/other split covers exactly
     the legal moves, (2) the counting sink agrees with the emitting one, (3) every clean move's fast reply count
     equals the full count of the child."""
-    parents, moves, clean, mismatches = incremental(oracle.parse(fen), max(0, depth - 2))
-    assert mismatches == 0 and parents > 0 and moves >= clean
+    parents, moves, clean, mismatches, inert = incremental(oracle.parse(fen), max(0, depth - 2))
+    assert mismatches == 0 and parents > 0 and moves >= clean >= inert
 
 
 def test_quiet_move_fast_path_on_playout_positions():
@@ -215,7 +215,7 @@ def test_quiet_move_fast_path_on_playout_positions():
         arr = oracle.random_playout(root, 0x1AC0000 + g, 200)
         for i in range(len(arr)):
             p = oracle.Position.from_buffer_copy(arr[i].tobytes())
-            parents, moves, clean, mismatches = incremental(p, 0)
+            parents, moves, clean, mismatches, inert = incremental(p, 0)
             assert mismatches == 0, oracle.to_fen(p)
             total += moves
             total_clean += clean
