@@ -28,8 +28,9 @@ namespace pabi {
 constexpr int META_BASE = 32;
 
 struct TContext {
-  u64 reach; /* union of T's slider attack sets: a clean move neither leaves nor lands on it; ~0 = no clean moves */
-  u64 guard; /* reach plus the king guard below: a clean move does not leave it, a clean slider move does not land on it */
+  u64 reach; /* union of T's slider attack sets plus the pieces that shield T's king from an S slider: a clean move
+                neither leaves nor lands on it; ~0 = no clean moves */
+  u64 guard; /* reach plus the king guard below: a clean slider move does not land on it */
   u64 zone;  /* squares T's pawn and king moves depend on: a clean move that also stays off it is INERT */
   u32 base;  /* moves of T's knights, bishops, rooks and queens in the parent position */
   u32 total; /* base + T's pawn and king moves in the parent position = the reply count of every inert move */
@@ -135,9 +136,18 @@ PB_HD TContext t_context(const Pos& n, const TB& tb) {
     base += popc(a & not_w & ((pins >> sq) & 1 ? tb.line(tk, sq) : ~0ULL));
   }
   c.guard = reach | tb.bishop(tk, occ & ~kd) | tb.rook(tk, occ & ~ko);
+  /* Leaving a square of a king line matters only if that uncovers an S slider: the square is one of at most
+   * two pieces between T's king and an S slider that moves along that line (with three or more, two still
+   * shield the king afterwards). */
+  u64 uncover = 0;
+  for (Squares b((tb.s->orth[tk] & s_orth) | ((tb.s->diag[tk] | tb.s->anti[tk]) & s_diag)); b.any();) {
+    const int sq = b.pop();
+    const u64 between = tb.ray(sq, tk) & occ & ~bit(sq);
+    if (popc(between) <= 2) uncover |= between;
+  }
   /* with a T piece pinned, a knight, pawn or king arriving between it and its pinner would free it:
    * such parents hold every mover to the full guard */
-  c.reach = pins ? c.guard : reach;
+  c.reach = pins ? c.guard : reach | uncover;
   c.base = base;
   /* Inert moves.  T's pawn moves depend on the squares in front of and diagonally ahead of its pawns; its king
    * moves on the king's neighbourhood (and the castling walks) and on every square from which a piece can see
@@ -175,12 +185,12 @@ PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 reach, u64 guard, Sin
   const u64 W = a.their;
   const u64 tk_bb = n.kings & W;
   const int tk = lsb(tk_bb);
-  /* a clean move leaves a square outside `guard`; a slider lands outside `guard`; a knight, pawn or king
+  /* a clean move leaves a square outside `reach`; a slider lands outside `guard`; a knight, pawn or king
    * outside `reach` (arriving on a king ray they change neither checks nor pins) */
   const u64 open = ~guard & ~W;
   const u64 open_leaper = ~reach & ~W;
   {
-    const u64 c = (guard >> a.king) & 1 ? 0 : a.safe_king & open_leaper;
+    const u64 c = (reach >> a.king) & 1 ? 0 : a.safe_king & open_leaper;
     sink.piece(a.king, KIND_KING, c, a.safe_king & ~c);
   }
   if (a.block == 0) return;
@@ -189,31 +199,33 @@ PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 reach, u64 guard, Sin
   for (Squares b(n.knights & a.our & ~a.pins); b.any();) {
     const int from = b.pop();
     const u64 t = tb.knight(from) & targets;
-    const u64 c = (guard >> from) & 1 ? 0 : t & open_leaper & ~tb.knight(tk); /* a knight on KNIGHT[tk] checks */
+    const u64 c = (reach >> from) & 1 ? 0 : t & open_leaper & ~tb.knight(tk); /* a knight on KNIGHT[tk] checks */
     sink.piece(from, KIND_KNIGHT, c, t & ~c);
   }
   for (Squares b((n.rooks | n.queens) & a.our); b.any();) {
     const int from = b.pop();
     u64 t = tb.rook(from, a.occ) & targets;
     if ((a.pins >> from) & 1) t &= tb.line(a.king, from);
-    const u64 c = (guard >> from) & 1 ? 0 : t & open; /* off the king's lines a slider cannot check */
+    const u64 c = (reach >> from) & 1 ? 0 : t & open; /* off the king's lines a slider cannot check */
     sink.piece(from, (n.queens >> from) & 1 ? KIND_QUEEN : KIND_ROOK, c, t & ~c);
   }
   for (Squares b((n.bishops | n.queens) & a.our); b.any();) {
     const int from = b.pop();
     u64 t = tb.bishop(from, a.occ) & targets;
     if ((a.pins >> from) & 1) t &= tb.line(a.king, from);
-    const u64 c = (guard >> from) & 1 ? 0 : t & open;
+    const u64 c = (reach >> from) & 1 ? 0 : t & open;
     sink.piece(from, (n.queens >> from) & 1 ? KIND_QUEEN : KIND_BISHOP, c, t & ~c);
   }
 
   /* pawns of the mover (black, moving down the board) */
   const PawnSets ps = pawn_sources(n, tb, a);
   const u64 capture_targets = W & a.block;
-  for (Squares b(ps.west | ps.east); b.any();) {
+  const u64 west_sources = ps.west & (capture_targets << 9) & ~FILE_A; /* black captures towards file a: from - 9 */
+  const u64 east_sources = ps.east & (capture_targets << 7) & ~FILE_H; /* towards file h: from - 7 */
+  for (Squares b(west_sources | east_sources); b.any();) {
     const int from = b.pop();
     const u64 from_bb = bit(from);
-    const u64 t = (pawn_attacks_west(from_bb & ps.west, 1) | pawn_attacks_east(from_bb & ps.east, 1)) & capture_targets;
+    const u64 t = (from_bb & west_sources) >> 9 | (from_bb & east_sources) >> 7;
     for (Squares ts(t); ts.any();) sink.pawn_capture(from, ts.pop());
   }
   if (meta_ep(n.meta) < NO_SQUARE)
@@ -225,8 +237,8 @@ PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 reach, u64 guard, Sin
   const u64 checks = pawn_attacks(tk_bb, 0);            /* squares from which a black pawn attacks T's king */
   const u64 t_pawns = n.pawns & W;
   const u64 beside_t_pawn = ((t_pawns & ~FILE_A) >> 1) | ((t_pawns & ~FILE_H) << 1); /* a double push there creates an en passant square */
-  const u64 c1 = single & open_leaper & ~(guard >> 8) & ~RANK_1 & ~checks;
-  const u64 c2 = dbl & open_leaper & ~(guard >> 16) & ~checks & ~beside_t_pawn;
+  const u64 c1 = single & open_leaper & ~(reach >> 8) & ~RANK_1 & ~checks;
+  const u64 c2 = dbl & open_leaper & ~(reach >> 16) & ~checks & ~beside_t_pawn;
   sink.pushes(c1, single & ~c1, 8);
   sink.pushes(c2, dbl & ~c2, 16);
   const int c = castle_moves(n, a);

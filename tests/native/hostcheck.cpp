@@ -249,6 +249,54 @@ void hostcheck_incremental(const pabi_position_t* root, int depth, uint64_t out[
   incremental_walk(pack_record(*root), host_tb(), depth, out);
 }
 
+/* Diagnostic for DESIGN.md: why moves miss the fast path.  For every node of the tree as a K2 parent, every legal
+ * move falls in one class: out[0] inert, [1] clean, [2] parent ineligible (T in check / pinned T pawn),
+ * [3] capture, [4] promotion / en passant / castling, [5] leaves the guard (from on a T slider line or king line),
+ * [6] lands on the guard or reach, [7] gives check by knight/pawn or creates an en passant square, [8] parents; [9] / [10] = the part of [5] / [6]
+ * that is on a T slider's attack set (the rest is on a king line only). */
+static void split_stats_walk(const Pos& p, const Tables& tb, int depth, uint64_t* out) {
+  Pos n = meta_stm(p.meta) == 0 ? mirror(p) : p;
+  const TContext ctx = t_context(n, tb);
+  ++out[8];
+  SplitCounter counter{ctx.zone};
+  enumerate_split(n, tb, ctx.reach, ctx.guard, counter);
+  out[0] += counter.inert, out[1] += counter.clean;
+  const u64 W = n.white;
+  generate_moves<1>(n, tb, [&](int f, int t, int pr, int kind) {
+    bool clean = false;
+    { /* is it clean?  ask the splitter through a one-move sink */
+      struct One { int f, t; bool hit = false;
+        void piece(int from, int, u64 c, u64) { if (from == f && ((c >> t) & 1)) hit = true; }
+        void pushes(u64 c, u64, int d) { if (f == t + d && ((c >> t) & 1)) hit = true; }
+        void pawn_capture(int, int) {} void en_passant(int, int) {} void castle(int, int) {} } one{f, t};
+      enumerate_split(n, tb, ctx.reach, ctx.guard, one);
+      clean = one.hit && pr == 0;
+    }
+    if (clean) return;
+    const bool castle = kind == KIND_KING && (f - t == 2 || t - f == 2);
+    const bool ep = kind == KIND_PAWN && t == meta_ep(n.meta) && ((f ^ t) & 7);
+    if (ctx.reach == ~0ULL) ++out[2];
+    else if ((W >> t) & 1) ++out[3];
+    else if (pr || ep || castle) ++out[4];
+    else if ((ctx.reach >> f) & 1) ++out[5], out[9] += (ctx.reach >> f) & 1;
+    else if (((kind == KIND_BISHOP || kind == KIND_ROOK || kind == KIND_QUEEN ? ctx.guard : ctx.reach) >> t) & 1) ++out[6], out[10] += (ctx.reach >> t) & 1;
+    else ++out[7];
+  });
+  if (depth == 0) return;
+  uint16_t mv[256];
+  uint32_t k = 0;
+  generate_moves(p, tb, [&](int f, int t, int pr, int) { mv[k++] = pack_move(f, t, pr); });
+  for (uint32_t i = 0; i < k; i++) {
+    Pos c = p;
+    make_move(c, tb, mv[i]);
+    split_stats_walk(c, tb, depth - 1, out);
+  }
+}
+void hostcheck_split_stats(const pabi_position_t* root, int depth, uint64_t out[11]) {
+  for (int i = 0; i < 11; i++) out[i] = 0;
+  split_stats_walk(pack_record(*root), host_tb(), depth, out);
+}
+
 /* table access for tests/test_tables*.py */
 const uint64_t* hostcheck_table(const char* name, size_t* count) {
   const HostTables& h = host_tables();

@@ -77,7 +77,8 @@ def outer(chain, fname):
         if fr.startswith(fname + ":"):
             return fr
     return chain[-1] if chain else "?"
-for fname, title in (("chess.cuh", "by outermost chess.cuh line (callers of the helpers)"), ("kernels.cuh", "by kernel line")):
+for fname, title in (("chess.cuh", "by outermost chess.cuh line (callers of the helpers)"),
+                     ("incremental.cuh", "by outermost incremental.cuh line (fast path and split enumeration)"), ("kernels.cuh", "by kernel line")):
     agg2 = defaultdict(lambda: [0, 0])
     for ch, r in zip(chains, body):
         k = outer(ch, fname)
