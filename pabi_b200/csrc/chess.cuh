@@ -265,7 +265,7 @@ struct Analysis {
  *    it is ours" (attacks.rs:147-156) is the same condition.
  *  - xrays (attacks.rs:93) are not computed: move generation never reads them. */
 template <int US = -1, class TB>
-PB_HD void analyze(const Pos& p, const TB& tb, Analysis& a) {
+PB_HD void analyze(const Pos& p, const TB& tb, Analysis& a, bool want_attacks = true) {
   const int us = US >= 0 ? US : meta_stm(p.meta); /* US: side to move when known at compile time */
   const int them = us ^ 1;
   const u64 occ = p.pawns | p.knights | p.bishops | p.rooks | p.queens | p.kings;
@@ -294,7 +294,7 @@ PB_HD void analyze(const Pos& p, const TB& tb, Analysis& a) {
     if ((rights & 2) && (occ & (0x0EULL << sh)) == 0) need |= 0x0CULL << sh;
   }
   u64 att = 0;
-  if (need) {
+  if (need && want_attacks) { /* a caller that will emit neither king nor castling moves skips the map */
     att = tb.king(lsb(p.kings & their)) | pawn_attacks(p.pawns & their, them);
     for (Squares b(p.knights & their & tb.s->knight_zone[king]); b.any();) att |= tb.knight(b.pop());
     for (Squares b(their_diag & tb.s->diag_zone[king]); b.any();) {

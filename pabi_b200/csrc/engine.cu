@@ -163,11 +163,11 @@ constexpr size_t FLAT_SMEM = sizeof(SharedTables);
  * choice can be re-measured on the device (environment variable PABI_TILE_VARIANT). */
 /* 1024 threads (64 registers each, 32 warps per SM) in four independent 256-thread groups that share one
  * table image: while one group scans / generates, the others count */
-using TileDefault = TileConfig<1024, 256, 5120, 1, 4>;
+using TileDefault = TileConfig<1024, 256, 4608, 1, 4>;
 using TileV1 = TileConfig<1024, 512, 8192, 1, 2>;
 using TileV2 = TileConfig<1024, 1024, 16384, 1, 1>;
-using TileV3 = TileConfig<1024, 256, 4608, 1, 4>;
-using TileV4 = TileConfig<1024, 128, 2560, 1, 8>;
+using TileV3 = TileConfig<1024, 256, 4096, 1, 4>;
+using TileV4 = TileConfig<1024, 128, 2304, 1, 8>;
 using TileV5 = TileConfig<768, 256, 6144, 1, 3>;
 constexpr int TILE_VARIANTS = 6;
 

@@ -721,6 +721,7 @@ struct TileGroupShared {
   u64 guard[CFG::PARENTS];      /* TILE_LEAF: TContext::guard of each parent (incremental.cuh) */
   u64 reach[CFG::PARENTS];      /* TILE_LEAF: TContext::reach */
   u64 zone[CFG::PARENTS];       /* TILE_LEAF: TContext::zone */
+  u64 active[CFG::PARENTS];     /* TILE_LEAF: SplitCounter::active */
   u32 offs[CFG::PARENTS + 1];   /* TILE_LEAF: packed exclusive prefix (other << 16 | clean) of the parents' move counts */
   u32 chunk;                    /* TILE_LEAF: parents per pool filling */
 };
@@ -836,11 +837,13 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
          * cnt packs (other << 16 | clean) move counts for one scan. */
         if (meta_stm(p.meta) == 0) p = mirror(p);
         const TContext ctx = t_context(p, tb);
-        p.meta = (with_king_squares(p) & ~(0xFFFFULL << META_BASE)) | ((u64)ctx.base << META_BASE);
+        p.meta = (with_king_squares(p) & ~(0xFFFFULL << META_BASE) & ~(0xFFULL << META_PARTS)) | ((u64)ctx.base << META_BASE);
         sh.guard[tid] = ctx.guard, sh.reach[tid] = ctx.reach, sh.zone[tid] = ctx.zone;
         SplitCounter counter{ctx.zone};
         enumerate_split(p, tb, ctx.reach, ctx.guard, counter);
         cnt = counter.other << 16 | counter.clean;
+        sh.active[tid] = counter.active;
+        p.meta |= (u64)counter.parts << META_PARTS;
         /* inert moves are settled here: each has ctx.total replies */
         inert_children += counter.inert;
         inert_nodes = counter.inert * ctx.total;
@@ -907,7 +910,8 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         if (cnt && (u32)tid >= a && (u32)tid < a + chunk) {
           /* the parent is re-read from shared memory so that it does not occupy registers during phase B */
           SplitEmitter emit{sh.pool, (off & 0xFFFF) - clean_base, clean_here + (off >> 16) - other_base, (u32)tid << 16, sh.zone[tid]};
-          enumerate_split(tile_parent(sh, tid), tb, sh.reach[tid], sh.guard[tid], emit);
+          const Pos p = tile_parent(sh, tid);
+          enumerate_split(p, tb, sh.reach[tid], sh.guard[tid], emit, sh.active[tid], (u32)(p.meta >> META_PARTS) & PART_ALL);
         }
         group_sync<SYNC>(group);
         for (u32 c = tid; c < end; c += GT) {

@@ -211,6 +211,29 @@ struct CheckSink {
   void castle(int from, int to) { full(from, to, 0, KIND_KING); }
 };
 
+/* what K2's SplitEmitter writes to the pool: every move except the inert ones */
+struct PoolSink {
+  u64 zone;
+  uint32_t k = 0;
+  uint32_t entries[1024];
+  void put(int from, int to, int promo, int kind, int cls) { entries[k++] = (uint32_t)cls << 31 | (uint32_t)kind << 28 | pack_move(from, to, promo); }
+  void other(int from, int to, int kind) {
+    if (kind == KIND_PAWN && to < 8) for (int pr = 4; pr >= 1; pr--) put(from, to, pr, kind, 1);
+    else put(from, to, 0, kind, 1);
+  }
+  void piece(int from, int kind, u64 c, u64 o) {
+    for (Squares t(c & ~inert_targets(zone, from, c)); t.any();) put(from, t.pop(), 0, kind, 0);
+    for (Squares t(o); t.any();) put(from, t.pop(), 0, kind, 1);
+  }
+  void pushes(u64 c, u64 o, int delta) {
+    for (Squares t(c & ~inert_pushes(zone, c, delta)); t.any();) { const int to = t.pop(); put(to + delta, to, 0, KIND_PAWN, 0); }
+    for (Squares t(o); t.any();) { const int to = t.pop(); other(to + delta, to, KIND_PAWN); }
+  }
+  void pawn_capture(int from, int to) { other(from, to, KIND_PAWN); }
+  void en_passant(int from, int to) { put(from, to, 0, KIND_PAWN, 1); }
+  void castle(int from, int to) { put(from, to, 0, KIND_KING, 1); }
+};
+
 static void incremental_walk(const Pos& p, const Tables& tb, int depth, uint64_t* out) {
   Pos n = meta_stm(p.meta) == 0 ? mirror(p) : p;
   const TContext ctx = t_context(n, tb);
@@ -221,6 +244,15 @@ static void incremental_walk(const Pos& p, const Tables& tb, int depth, uint64_t
   enumerate_split(n, tb, ctx.reach, ctx.guard, counter);
   ++out[0], out[1] += sink.k, out[2] += sink.clean, out[4] += sink.inert;
   if (counter.clean + counter.inert != sink.clean || counter.other != sink.other || counter.inert != sink.inert) ++out[3];
+  { /* the emitting pass restricted to the active pieces / parts writes the same pool entries */
+    PoolSink all{ctx.zone}, restricted{ctx.zone};
+    enumerate_split(n, tb, ctx.reach, ctx.guard, all);
+    enumerate_split(n, tb, ctx.reach, ctx.guard, restricted, counter.active, counter.parts);
+    if (all.k != counter.clean + counter.other || restricted.k != all.k) ++out[3];
+    else
+      for (uint32_t i = 0; i < all.k; i++) /* same order: the restriction only skips pieces without entries */
+        if (all.entries[i] != restricted.entries[i]) { ++out[3]; break; }
+  }
   /* the split covers exactly the legal moves */
   uint16_t want[256];
   uint32_t nw = 0;
