@@ -237,6 +237,10 @@ def run_gpu(args) -> None:
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          "peak_source": peaks["source"], "traffic": traffic, "traffic_note": traffic_note,
                          "limiter_from_ncu": issue,
+                         "frac_note": ("frac above 1 is expected: SURVEY.md 8d's byte model has every node of plies 1..d-1 written "
+                                       "to and read from HBM once, but the fused kernel never materialises the last ply but one "
+                                       "(and counts most of its moves per parent without making them), so its real DRAM traffic "
+                                       "is `traffic`; the unit that binds it is the integer ALU pipe (limiter_from_ncu)"),
                          "algorithmic_bytes_per_launch": leaf_bytes / max(1, leaf_launches),
                          "avg_launch_ms": leaf_ms / max(1, leaf_launches), "launches": leaf_launches,
                          "share_of_step": leaf_ms / device_ms if device_ms else None,
