@@ -148,6 +148,10 @@ def run_gpu(args) -> None:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
@@ -249,7 +253,7 @@ def run_gpu(args) -> None:
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_sample(os.cpu_count() or 1)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     engine.close()
     if world > 1:
         dist.destroy_process_group()
