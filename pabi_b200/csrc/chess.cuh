@@ -471,6 +471,10 @@ PB_HD PawnSets pawn_sources(const Pos& p, const TB& tb, const Analysis& a) {
  *  - our sliders hemmed in by our own pieces are skipped.
  * Every shortcut is exact; tests/test_device_logic_on_host.py compares the
  * result with the oracle's list length on every node of the reference trees. */
+/* the squares with a rank/file (diagonal) neighbour in `set`: a slider none of whose neighbours is free of
+ * its own pieces has no moves, and its attack set holds own pieces only */
+PB_HD u64 orth_neighbours(u64 set) { return (set >> 8) | (set << 8) | ((set >> 1) & ~FILE_H) | ((set << 1) & ~FILE_A); }
+PB_HD u64 diag_neighbours(u64 set) { return (((set >> 9) | (set << 7)) & ~FILE_H) | (((set >> 7) | (set << 9)) & ~FILE_A); }
 PB_HD u64 bswap64(u64 x) {
 #ifdef __CUDA_ARCH__
   const u32 lo = (u32)x, hi = (u32)(x >> 32);
@@ -559,8 +563,7 @@ PB_HD u32 count_moves_white(u64 our, u64 pawns, u64 knights, u64 bishops, u64 ro
   for (Squares b(knights & our & ~pins); b.any();) n += popc(tb.knight(b.pop()) & targets);
   /* sliders hemmed in by our own pieces (no neighbour on their lines that is not ours) have no
    * moves and need no lookup; found set-wise */
-  const u64 orth_open = (not_our >> 8) | (not_our << 8) | ((not_our >> 1) & ~FILE_H) | ((not_our << 1) & ~FILE_A);
-  const u64 diag_open = (((not_our >> 9) | (not_our << 7)) & ~FILE_H) | (((not_our >> 7) | (not_our << 9)) & ~FILE_A);
+  const u64 orth_open = orth_neighbours(not_our), diag_open = diag_neighbours(not_our);
   for (Squares b((rooks | queens) & our & orth_open); b.any();) {
     const int from = b.pop();
     u64 t = tb.rook(from, occ) & targets;

@@ -124,13 +124,14 @@ PB_HD TContext t_context(const Pos& n, const TB& tb) {
   u64 reach = 0;
   u32 base = 0;
   for (Squares b(n.knights & W & ~pins); b.any();) base += popc(tb.knight(b.pop()) & not_w);
-  for (Squares b((n.rooks | n.queens) & W); b.any();) {
+  /* sliders hemmed in by T's own pieces see only those: nothing for `reach`, nothing for `base` */
+  for (Squares b((n.rooks | n.queens) & W & orth_neighbours(not_w)); b.any();) {
     const int sq = b.pop();
     const u64 a = tb.rook(sq, occ);
     reach |= a;
     base += popc(a & not_w & ((pins >> sq) & 1 ? tb.line(tk, sq) : ~0ULL));
   }
-  for (Squares b((n.bishops | n.queens) & W); b.any();) {
+  for (Squares b((n.bishops | n.queens) & W & diag_neighbours(not_w)); b.any();) {
     const int sq = b.pop();
     const u64 a = tb.bishop(sq, occ);
     reach |= a;
@@ -202,6 +203,8 @@ PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 reach, u64 guard, Sin
   if (a.block == 0) return;
   const u64 targets = ~a.our & a.block;
   const u64 movers = a.our & active;
+  const u64 orth_movers = (n.rooks | n.queens) & movers & orth_neighbours(~a.our); /* hemmed-in sliders have no moves */
+  const u64 diag_movers = (n.bishops | n.queens) & movers & diag_neighbours(~a.our);
 
   for (Squares b(n.knights & movers & ~a.pins); b.any();) {
     const int from = b.pop();
@@ -209,14 +212,14 @@ PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 reach, u64 guard, Sin
     const u64 c = (reach >> from) & 1 ? 0 : t & open_leaper & ~tb.knight(tk); /* a knight on KNIGHT[tk] checks */
     sink.piece(from, KIND_KNIGHT, c, t & ~c);
   }
-  for (Squares b((n.rooks | n.queens) & movers); b.any();) {
+  for (Squares b(orth_movers); b.any();) {
     const int from = b.pop();
     u64 t = tb.rook(from, a.occ) & targets;
     if ((a.pins >> from) & 1) t &= tb.line(a.king, from);
     const u64 c = (reach >> from) & 1 ? 0 : t & open; /* off the king's lines a slider cannot check */
     sink.piece(from, (n.queens >> from) & 1 ? KIND_QUEEN : KIND_ROOK, c, t & ~c);
   }
-  for (Squares b((n.bishops | n.queens) & movers); b.any();) {
+  for (Squares b(diag_movers); b.any();) {
     const int from = b.pop();
     u64 t = tb.bishop(from, a.occ) & targets;
     if ((a.pins >> from) & 1) t &= tb.line(a.king, from);
