@@ -16,6 +16,8 @@ top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 # optional 5th argument "file:first-last": an extra table by the innermost frame inside that line range
 # (the lines of one function: where the time inside it goes, helpers folded into their call sites)
 span = sys.argv[5] if len(sys.argv) > 5 else None
+# optional 6th argument "file:line": restrict that extra table to instructions inlined below this call site
+within = sys.argv[6] if len(sys.argv) > 6 else None
 tmp = Path(tempfile.mkdtemp())
 subprocess.run(["cuobjdump", "-xelf", "all", str(Path(so).resolve())], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
 cubin = max(tmp.glob("*.cubin"), key=lambda p: p.stat().st_size)
@@ -95,11 +97,13 @@ if span:
     first, last = (int(x) for x in rng.split("-"))
     agg3 = defaultdict(lambda: [0, 0])
     for ch, r in zip(chains, body):
+        if within and within not in ch:
+            continue
         k = next((fr for fr in ch if fr.startswith(fname + ":") and first <= int(fr.split(":")[1]) <= last), None)
         if k:
             agg3[k][0] += int(r[col["Instructions Executed"]])
             agg3[k][1] += int(r[col["# Samples"]])
-    print(f"--- inside {span}, by its own lines ---")
+    print(f"--- inside {span}{' below ' + within if within else ''}, by its own lines ---")
     for where, (inst, samp) in sorted(agg3.items(), key=lambda kv: int(kv[0].split(":")[1])):
         if inst * 1000 >= tot_inst:
             print(f"{100*inst/tot_inst:5.1f}% inst {100*samp/max(1,tot_samp):5.1f}% samp  {where:18s} {src(where)}")
