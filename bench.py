@@ -219,7 +219,7 @@ def run_gpu(args) -> None:
             t = json.loads(prof.read_text())
             # what actually limits the kernel (ncu capture, not measured in this run): the integer ALU pipe
             issue = {k: t[k] for k in ("alu_pipe_pct_of_peak", "issue_active_pct", "xu_pipe_pct", "lsu_pipe_pct", "fma_pipe_pct",
-                                       "thread_inst_per_warp_inst", "l1_hit_rate_pct", "dram_throughput_pct") if k in t}
+                                       "thread_inst_per_warp_inst", "l1_hit_rate_pct", "shared_bank_conflict_pct", "dram_throughput_pct") if k in t}
             issue["source"] = t["source"]
             traffic = t["dram_bytes_per_parent"] * leaf_parents / leaf_launches
             traffic_note = (f"{t['dram_bytes_per_parent']:.1f} B/parent (dram__bytes_read+write of the ncu capture, "
