@@ -161,9 +161,11 @@ constexpr size_t FLAT_SMEM = sizeof(SharedTables);
 
 /* Tile-kernel geometries.  Variant 0 is the default; the others exist so that the
  * choice can be re-measured on the device (environment variable PABI_TILE_VARIANT). */
-/* 1024 threads (64 registers each, 32 warps per SM) in four independent 256-thread groups that share one
- * table image: while one group scans / generates, the others count */
-using TileDefault = TileConfig<1024, 256, 4608, 1, 4>;
+/* 1024 threads (64 registers each, 32 warps per SM) in two independent 512-thread groups that share one table
+ * image: while one group scans / generates, the other counts.  Measured on startpos perft(8) with the inert-move
+ * accounting in place: 2 x 512 parents, pool 9216: 45.8 ms; pool 8192: 46.0; pool 7168: 46.3; 4 x 256 parents,
+ * pool 4608 (the default before): 47.9; 1 x 1024 parents, pool 16384: 47.2; 3 x 256 on 768 threads: 48.9 */
+using TileDefault = TileConfig<1024, 512, 9216, 1, 2>;
 /* small frontiers: shorter tiles, so that every thread group of the grid gets some and the launch lasts a few
  * short tiles instead of one long one (K2 on 2 039 parents: 0.21 -> 0.06 ms) */
 using TileSmall = TileConfig<1024, 64, 4608, 1, 4>;
@@ -173,7 +175,11 @@ using TileV2 = TileConfig<1024, 1024, 16384, 1, 1>;
 using TileV3 = TileConfig<1024, 256, 4096, 1, 4>;
 using TileV4 = TileConfig<1024, 128, 2304, 1, 8>;
 using TileV5 = TileConfig<768, 256, 6144, 1, 3>;
-constexpr int TILE_VARIANTS = 6;
+using TileV10 = TileConfig<1024, 512, 6144, 1, 2>;
+using TileV11 = TileConfig<1024, 512, 4608, 1, 2>;
+using TileV12 = TileConfig<1024, 512, 7168, 1, 2>;
+using TileV13 = TileConfig<1024, 256, 4608, 1, 4>;
+constexpr int TILE_VARIANTS = 14;
 
 /* prefix[0..n] = exclusive scan of counts[0..n) */
 void scan_counts(pabi_cuda_ctx* ctx, const u32* counts, size_t n, u64* prefix);
@@ -252,6 +258,10 @@ void launch_leaf(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n) {
       case 3: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV3>(ctx, in, 0, n, nullptr, out); break;
       case 4: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV4>(ctx, in, 0, n, nullptr, out); break;
       case 5: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV5>(ctx, in, 0, n, nullptr, out); break;
+      case 10: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV10>(ctx, in, 0, n, nullptr, out); break;
+      case 11: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV11>(ctx, in, 0, n, nullptr, out); break;
+      case 12: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV12>(ctx, in, 0, n, nullptr, out); break;
+      case 13: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV13>(ctx, in, 0, n, nullptr, out); break;
       default: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileDefault>(ctx, in, 0, n, nullptr, out); break;
     }
   }

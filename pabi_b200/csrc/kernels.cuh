@@ -723,7 +723,6 @@ struct TileGroupShared {
   u64 zone[CFG::PARENTS];       /* TILE_LEAF: TContext::zone */
   u64 active[CFG::PARENTS];     /* TILE_LEAF: SplitCounter::active */
   u32 offs[CFG::PARENTS + 1];   /* TILE_LEAF: packed exclusive prefix (other << 16 | clean) of the parents' move counts */
-  u32 chunk;                    /* TILE_LEAF: parents per pool filling */
 };
 
 template <class CFG>
@@ -878,36 +877,35 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
     }
 
     if (LEAF) {
-      /* The pool is filled once per CHUNK of parents: the largest power-of-two fraction of the tile whose
-       * children fit, so that every parent enumerates its moves exactly once.  Inside a chunk the clean
-       * children come first, the others follow. */
-      static_assert(!LEAF || (PARENTS & (PARENTS - 1)) == 0, "K2 halves its tiles");
+      /* The pool is filled once per CHUNK of consecutive parents, so that every parent enumerates its moves
+       * exactly once.  A tile whose entries do not fit is cut into the smallest number of chunks of about equal
+       * size (every thread finds the same boundaries by binary search in the prefix array).  Inside a chunk the
+       * clean children come first, the others follow. */
+      static_assert(POOL >= 1024, "a chunk leaves room for one more parent's moves");
       if (tid < PARENTS) sh.offs[tid] = off;
-      if (tid == 0) {
-        const u32 packed_total = (total - clean_total) << 16 | clean_total;
-        sh.offs[PARENTS] = packed_total;
-      }
+      if (tid == 0) sh.offs[PARENTS] = (total - clean_total) << 16 | clean_total;
       group_sync<SYNC>(group);
-      if (tid == 0) {
-        u32 chunk = PARENTS;
-        for (; chunk > 1; chunk >>= 1) {
-          bool fits = true;
-          for (u32 a = 0; a < (u32)PARENTS && fits; a += chunk) {
-            const u32 lo = sh.offs[a], hi = sh.offs[a + chunk];
-            fits = ((hi & 0xFFFF) - (lo & 0xFFFF)) + ((hi >> 16) - (lo >> 16)) <= (u32)POOL;
+      const auto entries_before = [&](u32 b) { const u32 v = sh.offs[b]; return (v & 0xFFFF) + (v >> 16); };
+      const u32 n_chunks = total <= (u32)POOL ? 1 : (total + (POOL - 256) - 1) / (POOL - 256); /* a parent has < 256 moves */
+      u32 a = 0;
+      for (u32 j = 1; j <= n_chunks; j++) {
+        u32 b = PARENTS; /* chunk j: the parents [a, b) whose entries end within the first j / n_chunks of the tile's */
+        if (j < n_chunks) {
+          const u32 limit = (u32)(((u64)total * j) / n_chunks);
+          u32 lo_b = a, hi_b = PARENTS; /* largest b with entries_before(b) <= limit */
+          while (lo_b < hi_b) {
+            const u32 mid = (lo_b + hi_b + 1) >> 1;
+            if (entries_before(mid) <= limit) lo_b = mid; else hi_b = mid - 1;
           }
-          if (fits) break;
+          b = lo_b;
         }
-        sh.chunk = chunk;
-      }
-      group_sync<SYNC>(group);
-      const u32 chunk = sh.chunk;
-      for (u32 a = 0; a < (u32)PARENTS; a += chunk) {
-        const u32 lo = sh.offs[a], hi = sh.offs[a + chunk];
+        const u32 lo = sh.offs[a], hi = sh.offs[b];
         const u32 clean_base = lo & 0xFFFF, other_base = lo >> 16;
         const u32 clean_here = (hi & 0xFFFF) - clean_base, end = clean_here + (hi >> 16) - other_base;
+        const u32 chunk_first = a;
+        a = b;
         if (end == 0) continue;
-        if (cnt && (u32)tid >= a && (u32)tid < a + chunk) {
+        if (cnt && (u32)tid >= chunk_first && (u32)tid < b) {
           /* the parent is re-read from shared memory so that it does not occupy registers during phase B */
           SplitEmitter emit{sh.pool, (off & 0xFFFF) - clean_base, clean_here + (off >> 16) - other_base, (u32)tid << 16, sh.zone[tid]};
           const Pos p = tile_parent(sh, tid);
