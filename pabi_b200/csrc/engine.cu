@@ -170,16 +170,12 @@ using TileDefault = TileConfig<1024, 512, 9216, 1, 2>;
  * short tiles instead of one long one (K2 on 2 039 parents: 0.21 -> 0.06 ms) */
 using TileSmall = TileConfig<1024, 64, 4608, 1, 4>;
 using TileTiny = TileConfig<1024, 32, 2048, 1, 4>;
-using TileV1 = TileConfig<1024, 512, 8192, 1, 2>;
-using TileV2 = TileConfig<1024, 1024, 16384, 1, 1>;
-using TileV3 = TileConfig<1024, 256, 4096, 1, 4>;
-using TileV4 = TileConfig<1024, 128, 2304, 1, 8>;
-using TileV5 = TileConfig<768, 256, 6144, 1, 3>;
-using TileV10 = TileConfig<1024, 512, 6144, 1, 2>;
-using TileV11 = TileConfig<1024, 512, 4608, 1, 2>;
-using TileV12 = TileConfig<1024, 512, 7168, 1, 2>;
-using TileV13 = TileConfig<1024, 256, 4608, 1, 4>;
-constexpr int TILE_VARIANTS = 14;
+using TileV1 = TileConfig<1024, 256, 4608, 1, 4>;   /* four 256-parent groups: the default before the inert-move accounting */
+using TileV2 = TileConfig<1024, 1024, 16384, 1, 1>; /* one group */
+using TileV3 = TileConfig<1024, 512, 7168, 1, 2>;   /* the default with a smaller pool (more L1) */
+using TileV4 = TileConfig<1024, 128, 2304, 1, 8>;   /* eight groups */
+using TileV5 = TileConfig<768, 256, 6144, 1, 3>;    /* 768 threads: 80 registers, no spills */
+constexpr int TILE_VARIANTS = 6;
 
 /* prefix[0..n] = exclusive scan of counts[0..n) */
 void scan_counts(pabi_cuda_ctx* ctx, const u32* counts, size_t n, u64* prefix);
@@ -258,10 +254,6 @@ void launch_leaf(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n) {
       case 3: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV3>(ctx, in, 0, n, nullptr, out); break;
       case 4: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV4>(ctx, in, 0, n, nullptr, out); break;
       case 5: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV5>(ctx, in, 0, n, nullptr, out); break;
-      case 10: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV10>(ctx, in, 0, n, nullptr, out); break;
-      case 11: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV11>(ctx, in, 0, n, nullptr, out); break;
-      case 12: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV12>(ctx, in, 0, n, nullptr, out); break;
-      case 13: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileV13>(ctx, in, 0, n, nullptr, out); break;
       default: launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, TileDefault>(ctx, in, 0, n, nullptr, out); break;
     }
   }
