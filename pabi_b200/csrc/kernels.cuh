@@ -688,19 +688,24 @@ __global__ void k_dedup_compact(const u64* __restrict__ rec, size_t stride, size
 }
 
 /* ---- K1 / K2: tile kernels ------------------------------------------------
- * A block takes PARENTS consecutive parents at a time:
- *   A0  threads 0..PARENTS-1 count the moves of their parent; block exclusive scan
- *   A   the same threads generate their parent's moves (reference order) into the
- *       shared pool at the scanned offset, as (kind << 28 | parent << 16 | move)
- *   B   every thread takes children from the pool: parent record from shared
- *       memory, make_move in registers, then
- *         K1: store the child record (coalesced SoA) at its global offset
- *         K2: count the child's moves and accumulate -- the children are never
- *             written to HBM
- * If a tile has more children than the pool holds, A/B repeat over windows.
- * The geometry (threads, parents per tile, pool entries, blocks per SM) is a
- * template parameter so that variants can be timed against each other on the
- * device (PABI_TILE_VARIANT, see engine.cu). */
+ * A thread group takes PARENTS consecutive parents at a time:
+ *   A0  threads 0..PARENTS-1 size their parent's move list; group exclusive scan.
+ *       K1 / K3 read the sizes from the global scan (k_count + k_scan_*).
+ *       K2 computes them itself with enumerate_split (incremental.cuh), which also
+ *       settles the parent's INERT moves on the spot (replies = inert x total) and
+ *       splits the rest into clean and other
+ *   A   the same threads write their parent's moves into the shared pool at the scanned
+ *       offset, as (kind << 28 | parent << 16 | move); K2: clean entries from the front,
+ *       the others behind them, a tile that does not fit in equal chunks of parents;
+ *       K1 / K3: reference order, sliding windows
+ *   B   every thread takes entries from the pool, parent record from shared memory:
+ *         K1: make_move in registers, store the child record (coalesced SoA) at its
+ *             global offset
+ *         K2: clean entry -> count_child_fast; other -> make_move_kind in registers and
+ *             the full count; accumulate -- the children are never written to HBM
+ * The geometry (threads, groups, parents per tile, pool entries) is a template parameter
+ * so that variants can be timed against each other on the device (PABI_TILE_VARIANT,
+ * see engine.cu). */
 /* THREADS threads per block in GROUPS independent groups; each group works on tiles of PARENTS
  * parents with its own pool of POOL entries. */
 template <int THREADS_, int PARENTS_, int POOL_, int MIN_BLOCKS_, int GROUPS_ = 1>
@@ -974,10 +979,11 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
  * warp shuffle scan, generation into the warp's private pool, then the 32 lanes walk the pool.  No
  * block-wide barrier, no idle group while the slowest parent of 256 finishes generating; tiles come
  * from the ticket counter.  Pool entries are 3 bytes: the move, and kind << 5 | parent.
- * Measured (B200, startpos perft(8)): 107.8 ms, the same as the block-level kernel with four groups
- * and tickets (107.8 ms) -- once tiles are scheduled dynamically the barrier waits are hidden by the
+ * Measured (B200, startpos perft(8), before the fast paths of incremental.cuh existed): 107.8 ms, the same as the
+ * block-level kernel with four 256-thread groups and tickets (107.8 ms) -- once tiles are scheduled dynamically the barrier waits are hidden by the
  * other groups and both versions sit on the ALU-pipe limit of count_moves_white.  The block-level kernel
- * stays the default because it also serves K1 and the per-root / weighted accountings; this one is
+ * stays the default because it also serves K1 and the per-root / weighted accountings, and it alone got the
+ * quiet-move fast paths afterwards (45.8 ms); this one is kept as the plain reference formulation of K2,
  * selectable with PABI_TILE_VARIANT=8. */
 constexpr int LEAFW_THREADS = 1024;
 constexpr int LEAFW_POOL = 1152; /* entries per warp; 32 parents average ~830 children in the start-position tree */

@@ -84,14 +84,17 @@ def outer(chain, fname):
     return chain[-1] if chain else "?"
 for fname, title in (("chess.cuh", "by outermost chess.cuh line (callers of the helpers)"),
                      ("incremental.cuh", "by outermost incremental.cuh line (fast path and split enumeration)"), ("kernels.cuh", "by kernel line")):
-    agg2 = defaultdict(lambda: [0, 0])
+    agg2 = defaultdict(lambda: [0, 0, 0])
+    tcol = col.get("Thread Instructions Executed")
     for ch, r in zip(chains, body):
         k = outer(ch, fname)
         agg2[k][0] += int(r[col["Instructions Executed"]])
         agg2[k][1] += int(r[col["# Samples"]])
-    print(f"--- {title} ---")
-    for where, (inst, samp) in sorted(agg2.items(), key=lambda kv: -kv[1][0])[:top]:
-        print(f"{100*inst/tot_inst:5.1f}% inst {100*samp/max(1,tot_samp):5.1f}% samp  {where:18s} {src(where)}")
+        if tcol is not None:
+            agg2[k][2] += int(r[tcol])
+    print(f"--- {title} (lanes = active threads per warp instruction) ---")
+    for where, (inst, samp, thr) in sorted(agg2.items(), key=lambda kv: -kv[1][0])[:top]:
+        print(f"{100*inst/tot_inst:5.1f}% inst {100*samp/max(1,tot_samp):5.1f}% samp {thr/max(1,inst):5.1f} lanes  {where:18s} {src(where)}")
 if span:
     fname, rng = span.split(":")
     first, last = (int(x) for x in rng.split("-"))
