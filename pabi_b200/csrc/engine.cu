@@ -326,8 +326,39 @@ size_t merge_transpositions(pabi_cuda_ctx* ctx, int lv, size_t n) {
 /* Walks `remaining` plies below the n records of level `lv`, adding leaf counts
  * to d_nodes (per root for PER_ROOT; times the record's multiplicity for WEIGHTED, where every
  * expanded chunk is passed through merge_transpositions). */
+/* Up to max_plies plies below the n records of level lv in ONE launch, as long as the frontier stays within one
+ * block (k_root_levels): returns the plies done and leaves the size of the frontier of level lv + plies in n. */
+int root_levels(pabi_cuda_ctx* ctx, int lv, size_t& n, int max_plies, Accounting acc) {
+  if (acc == WEIGHTED || n == 0 || n > (size_t)ROOT_THREADS || ctx->capacity < (size_t)ROOT_THREADS * 256) return 0;
+  if (max_plies > ROOT_MAX_PLIES) max_plies = ROOT_MAX_PLIES;
+  if (lv + max_plies >= MAX_LEVELS) max_plies = MAX_LEVELS - 1 - lv;
+  if (max_plies <= 0) return 0;
+  RootLevels levels;
+  levels.level[0] = frontier_of(ctx->levels[lv]);
+  for (int k = 1; k <= max_plies; k++) {
+    alloc_level(ctx, ctx->levels[lv + k], ctx->capacity);
+    levels.level[k] = frontier_of(ctx->levels[lv + k]);
+  }
+  if (acc == PER_ROOT) k_root_levels<true><<<1, ROOT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, levels, (u32)n, max_plies, ctx->d_result);
+  else k_root_levels<false><<<1, ROOT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, levels, (u32)n, max_plies, ctx->d_result);
+  LAUNCHED();
+  CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result, 3 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  n = (size_t)ctx->h_result[1];
+  ctx->interior += ctx->h_result[2];
+  return (int)ctx->h_result[0];
+}
+
 void descend(pabi_cuda_ctx* ctx, int lv, size_t n, int remaining, Accounting acc) {
   if (n == 0) return;
+  if (remaining > 2) { /* the launch-bound top of the tree: several plies per launch, two are left for K2 */
+    size_t below = n;
+    const int plies = root_levels(ctx, lv, below, remaining - 2, acc);
+    if (plies) {
+      descend(ctx, lv + plies, below, remaining - plies, acc);
+      return;
+    }
+  }
   ctx->interior += n;
   if (remaining == 1) {
     Level& cur = ctx->levels[lv];
@@ -464,6 +495,14 @@ int perft_impl(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, int d
       int plies = (int)split_ply;
       if (plies > depth - 1) plies = depth - 1;
       for (int s = 0; s < plies && cnt; s++) {
+        {
+          size_t below = cnt;
+          const int done = root_levels(ctx, lv, below, plies - s, acc);
+          if (done) {
+            cnt = below, lv += done, remaining -= done, s += done - 1;
+            continue;
+          }
+        }
         Level& cur = ctx->levels[lv];
         Level& next = ctx->levels[lv + 1];
         count_and_scan(ctx, cur.rec, cur.cap, 0, cnt, cur.counts, cur.prefix);
@@ -542,6 +581,8 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     CK(cudaMallocHost(&ctx->h_result, 4 * sizeof(u64)));
     /* kernels that stage the table image need more than the default 48 KB of dynamic shared memory */
     CK(cudaFuncSetAttribute(k_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_root_levels<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_root_levels<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_count_accumulate<SINGLE_ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_count_accumulate<PER_ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_count_accumulate<WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));

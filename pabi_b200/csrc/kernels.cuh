@@ -552,6 +552,56 @@ k_scan_down(const u32* __restrict__ in, size_t n, const u64* __restrict__ tile_s
   }
 }
 
+/* ---- the first plies of a walk, one launch ------------------------------------------------
+ * While a frontier has at most ROOT_THREADS records, one block expands it ply after ply (count,
+ * block scan, make the moves, store the children in the reference's order) without returning to
+ * the host: the launch-bound top of a perft tree (root -> 20 -> 400 -> 8 902 for the start
+ * position) costs one launch instead of six per ply.  result = {plies done, size of the last
+ * frontier written, records expanded}. */
+constexpr int ROOT_THREADS = 1024;
+constexpr int ROOT_MAX_PLIES = 8;
+struct RootLevels {
+  Frontier level[ROOT_MAX_PLIES + 1];
+};
+
+template <bool MULTI_ROOT>
+__global__ void __launch_bounds__(ROOT_THREADS, 1)
+k_root_levels(DeviceTables dt, RootLevels lv, u32 n, int max_plies, u64* __restrict__ result) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SharedTables* sh = reinterpret_cast<SharedTables*>(smem);
+  stage_tables(sh, dt.image);
+  const Tables tb{sh, dt.g};
+  __shared__ u32 warp_sums[ROOT_THREADS / 32 + 1];
+  const int tid = threadIdx.x;
+  int plies = 0;
+  u64 expanded = 0;
+  while (plies < max_plies && n && n <= (u32)ROOT_THREADS) {
+    const Frontier cur = lv.level[plies], next = lv.level[plies + 1];
+    Pos p;
+    u32 cnt = 0, total;
+    if ((u32)tid < n) {
+      p = load_pos(cur.rec, cur.stride, tid);
+      cnt = count_moves(p, tb);
+    }
+    u32 off = block_exclusive_scan<ROOT_THREADS>(cnt, warp_sums, total);
+    if (cnt) {
+      const u32 root = MULTI_ROOT ? cur.roots[tid] : 0;
+      generate_moves(p, tb, [&](int from, int to, int promo, int) {
+        Pos q = p;
+        make_move(q, tb, pack_move(from, to, promo));
+        store_pos(next.rec, next.stride, off, q);
+        if (MULTI_ROOT) next.roots[off] = root;
+        ++off;
+      });
+    }
+    expanded += n;
+    n = total;
+    ++plies;
+    __syncthreads(); /* the children are the next ply's parents (same block: visible after the barrier) */
+  }
+  if (tid == 0) result[0] = (u64)plies, result[1] = n, result[2] = expanded;
+}
+
 /* Largest end in [start, n] with prefix[end] - prefix[start] <= capacity; result {end, children}. */
 __global__ void k_chunk_end(const u64* __restrict__ prefix, size_t start, size_t n, u64 capacity, u64* __restrict__ result) {
   if (threadIdx.x || blockIdx.x) return;
