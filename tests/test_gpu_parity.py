@@ -125,6 +125,10 @@ def test_perft_batch_matches_oracle_per_root(engine, playout_positions):
         got = engine.perft_batch(batch, depth)
         want = [oracle.perft(oracle.Position.from_buffer_copy(batch[i].tobytes()), depth) for i in range(len(batch))]
         assert got.tolist() == want, depth
+    # few roots, deeper: several plies run inside the one-block root kernel, which has to carry the root indices
+    few = np.ascontiguousarray(batch[:9])
+    got = engine.perft_batch(few, 4)
+    assert got.tolist() == [oracle.perft(oracle.Position.from_buffer_copy(few[i].tobytes()), 4) for i in range(len(few))]
 
 
 def test_perft_batch_chunked(small_engine, playout_positions):
