@@ -384,6 +384,35 @@ def test_chess324_book_perft4_bit_exact(engine):
     assert sum(want) > 500_000_000
 
 
+def colour_flipped(pb, p):
+    """The same position seen from the other side: boards mirrored top to bottom, colours, castling rights and the
+    side to move swapped.  Chess is symmetric under this map, so every perft count is preserved."""
+    def flip(b):
+        return int.from_bytes(int(b).to_bytes(8, "little"), "big")  # rank 1 <-> rank 8
+    q = pb.Position()
+    r, o = q.raw, p.raw
+    for k in range(6):
+        r.white[k], r.black[k] = flip(o.black[k]), flip(o.white[k])
+    r.castling = ((o.castling & 3) << 2) | (o.castling >> 2)
+    r.side_to_move = o.side_to_move ^ 1
+    r.halfmove_clock, r.fullmove_counter = o.halfmove_clock, o.fullmove_counter
+    r.en_passant_square = 64 if o.en_passant_square >= 64 else o.en_passant_square ^ 56
+    return q
+
+
+def test_colour_symmetry_at_full_size(pb, engine, vectors):
+    """A size-independent property at the sizes the oracle cannot reach in seconds: the colour-flipped position has
+    the same perft count (the kernels take different code paths for it: the K2 parents are mirrored or not)."""
+    big = [c for c in vectors["perft"] + vectors["bench_perft"] if 50_000_000 < c["nodes"] < 1_000_000_000]
+    assert len(big) >= 5
+    for case in big:
+        p = fen_pos(pb, case["fen"])
+        assert engine.perft(colour_flipped(pb, p), case["depth"]) == case["nodes"], case
+    # and per root over a batch
+    flipped = [colour_flipped(pb, fen_pos(pb, c["fen"])) for c in big[:4]]
+    assert engine.perft_batch(flipped, 4).tolist() == engine.perft_batch([fen_pos(pb, c["fen"]) for c in big[:4]], 4).tolist()
+
+
 def test_one_million_move_lists_bit_exact(engine):
     """configs[4]: ordered move lists for 1M random-playout positions, bit-exact vs the oracle."""
     import workloads
