@@ -72,6 +72,22 @@ class Move:
         return hash(self.raw)
 
 
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """An uninitialised numpy array in page-locked host memory (`pabi_cuda_host_alloc`): positions, move lists and
+    counts that live in such arrays cross the PCIe link without the driver's staging copy."""
+    import weakref
+    dt = np.dtype(dtype)
+    count = int(np.prod(shape))
+    ptr = C.c_void_p()
+    rc = _native.lib().pabi_cuda_host_alloc(max(1, count * dt.itemsize), C.byref(ptr))
+    if rc != 0:
+        raise PabiCudaError(rc, "pabi_cuda_host_alloc failed")
+    buf = (C.c_uint8 * max(1, count * dt.itemsize)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dt, count=count).reshape(shape)
+    weakref.finalize(buf, _native.lib().pabi_cuda_host_free, ptr.value)  # buf stays alive as long as a view of it does
+    return arr
+
+
 def _as_array(positions) -> np.ndarray:
     """Sequence of Position / structured array -> contiguous POSITION_DTYPE array."""
     if isinstance(positions, np.ndarray):
@@ -154,12 +170,14 @@ class Engine:
         return [(Move.from_raw(moves[i]), int(nodes[i])) for i in range(n.value)]
 
     # -- batched move generation ----------------------------------------------
-    def generate_moves_batch(self, positions) -> Tuple[np.ndarray, np.ndarray]:
-        """CSR move lists: (offsets[n+1] u32, moves u16) in the reference's order."""
+    def generate_moves_batch(self, positions, offsets_out: Optional[np.ndarray] = None,
+                             moves_out: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """CSR move lists: (offsets[n+1] u32, moves u16) in the reference's order.  `offsets_out` / `moves_out`
+        (e.g. from `pinned_empty`) are used when given and large enough."""
         arr = _as_array(positions)
         n = len(arr)
-        offsets = np.empty(n + 1, dtype=np.uint32)
-        moves = np.empty(max(256, 40 * n), dtype=np.uint16)  # ~28 moves per position on playout positions
+        offsets = offsets_out if offsets_out is not None and len(offsets_out) >= n + 1 else np.empty(n + 1, dtype=np.uint32)
+        moves = moves_out if moves_out is not None else np.empty(max(256, 40 * n), dtype=np.uint16)  # ~28 moves per playout position
         t = Timing()
         L = _native.lib()
         rc = L.pabi_cuda_generate_moves_batch(self._ctx, arr.ctypes.data, n, offsets.ctypes.data, moves.ctypes.data,
@@ -170,7 +188,7 @@ class Engine:
                                                   len(moves), C.byref(t))
         self._check(rc)
         self.last_timing = t
-        return offsets, moves[: int(offsets[n])]
+        return offsets[: n + 1], moves[: int(offsets[n])]
 
     def count_moves_batch(self, positions) -> np.ndarray:
         arr = _as_array(positions)

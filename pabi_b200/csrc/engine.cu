@@ -643,6 +643,18 @@ void pabi_cuda_destroy(pabi_cuda_ctx* ctx) {
 const char* pabi_cuda_last_error(pabi_cuda_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
 int pabi_cuda_device(const pabi_cuda_ctx* ctx) { return ctx ? ctx->device : -1; }
 
+int pabi_cuda_host_alloc(size_t bytes, void** out) {
+  if (!out) return -1;
+  *out = nullptr;
+  const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (e != cudaSuccess) cudaGetLastError();
+  return (int)e;
+}
+
+void pabi_cuda_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+
 int pabi_cuda_perft(pabi_cuda_ctx* ctx, const pabi_position_t* root, uint8_t depth, uint64_t* nodes, pabi_timing_t* timing) {
   if (!ctx || !root || !nodes) return bad_arg(ctx, "null argument");
   return perft_impl(ctx, root, 1, depth, nodes, SINGLE_ROOT, 0, 0, 1, timing);

@@ -60,6 +60,8 @@ extern "C" {
     pub fn pabi_cuda_destroy(ctx: *mut Ctx);
     pub fn pabi_cuda_last_error(ctx: *mut Ctx) -> *const c_char;
     pub fn pabi_cuda_device(ctx: *const Ctx) -> i32;
+    pub fn pabi_cuda_host_alloc(bytes: usize, out: *mut *mut std::ffi::c_void) -> i32;
+    pub fn pabi_cuda_host_free(ptr: *mut std::ffi::c_void);
 
     pub fn pabi_cuda_perft(ctx: *mut Ctx, root: *const RawPosition, depth: u8, nodes: *mut u64, t: *mut Timing) -> i32;
     pub fn pabi_cuda_perft_hashed(ctx: *mut Ctx, root: *const RawPosition, depth: u8, nodes: *mut u64, t: *mut Timing) -> i32;

@@ -192,6 +192,20 @@ def test_move_lists_bit_exact_on_playout_positions(engine, playout_positions):
     assert np.array_equal(counts, np.diff(want_offsets))
 
 
+def test_page_locked_host_arrays(pb, engine, playout_positions):
+    """pabi_cuda_host_alloc: the batched calls give the same answers from and into page-locked arrays."""
+    n = 5000
+    src = np.ascontiguousarray(playout_positions[:n])
+    pinned = pb.pinned_empty(n, src.dtype)
+    pinned[:] = src
+    offsets_out, moves_out = pb.pinned_empty(n + 1, np.uint32), pb.pinned_empty(64 * n, np.uint16)
+    offsets, moves = engine.generate_moves_batch(pinned, offsets_out, moves_out)
+    want_offsets, want_moves = oracle.generate_moves_batch(src)
+    assert np.array_equal(offsets, want_offsets) and np.array_equal(moves, want_moves)
+    assert np.shares_memory(moves, moves_out) and np.shares_memory(offsets, offsets_out)
+    assert np.array_equal(engine.count_moves_batch(pinned), np.diff(want_offsets))
+
+
 def test_empty_and_tiny_batches(engine, playout_positions):
     offsets, moves = engine.generate_moves_batch(playout_positions[:0])
     assert offsets.tolist() == [0] and len(moves) == 0

@@ -66,6 +66,16 @@ t = e.last_timing
 print(json.dumps({"config": "move lists, 1M playout positions", "moves": int(len(moves)), "device_ms": round(dev, 4),
                   "e2e_ms": round(wall, 3), "positions_per_s_device": round(1e6 / dev * 1e3), "algorithmic_bytes": t.algorithmic_bytes,
                   "achieved_gbs": round(t.algorithmic_bytes / dev / 1e6, 1)}))
+# the same call with every host array in page-locked memory (pabi_cuda_host_alloc)
+pinned_in = pb.pinned_empty(len(positions), positions.dtype)
+pinned_in[:] = positions
+pinned_offsets = pb.pinned_empty(len(positions) + 1, np.uint32)
+pinned_moves = pb.pinned_empty(40 * len(positions), np.uint16)
+dev, wall, (offsets, moves) = best(lambda: e.generate_moves_batch(pinned_in, pinned_offsets, pinned_moves), reps=3)
+assert np.array_equal(offsets, want_offsets) and np.array_equal(moves, want_moves)
+print(json.dumps({"config": "move lists, 1M playout positions, host arrays page-locked", "device_ms": round(dev, 4), "e2e_ms": round(wall, 3),
+                  "h2d_bytes": int(pinned_in.nbytes), "d2h_bytes": int(offsets.nbytes + moves.nbytes),
+                  "positions_per_s_e2e": round(1e6 / wall * 1e3)}))
 t0 = time.perf_counter()
 oracle.generate_moves_batch(positions)
 print(json.dumps({"config": "move lists, 1M playout positions, oracle on 1 host core", "ms": round((time.perf_counter() - t0) * 1e3, 1)}))
