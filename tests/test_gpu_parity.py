@@ -427,6 +427,25 @@ def test_colour_symmetry_at_full_size(pb, engine, vectors):
     assert engine.perft_batch(flipped, 4).tolist() == engine.perft_batch([fen_pos(pb, c["fen"]) for c in big[:4]], 4).tolist()
 
 
+def test_command_line(pb):
+    """python -m pabi_b200: the OpenBench line the reference's `openbench()` is meant to print (src/engine/mod.rs:176-190,
+    tests/integration.rs:23-34: "<nodes> nodes <nps> nps") over the positions of benches/chess.rs:52-86, and perft divide."""
+    import re
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, "-m", "pabi_b200", "bench"], cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-1000:]
+    m = re.fullmatch(r"(\d+) nodes (\d+) nps", out.stdout.strip().splitlines()[-1])
+    assert m and int(m.group(1)) == 1_461_874_231 and int(m.group(2)) > 0
+    out = subprocess.run([sys.executable, "-m", "pabi_b200", "perft", "--depth", "3", "--divide", "--fen", KIWIPETE], cwd=root,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-1000:]
+    lines = out.stdout.strip().splitlines()
+    assert lines[-1] == "Nodes searched: 97862" and len(lines) == 48 + 2 and lines[0].startswith("e1d1: ")
+
+
 def test_one_million_move_lists_bit_exact(engine):
     """configs[4]: ordered move lists for 1M random-playout positions, bit-exact vs the oracle."""
     import workloads
