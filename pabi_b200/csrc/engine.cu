@@ -163,15 +163,16 @@ constexpr size_t FLAT_SMEM = sizeof(SharedTables);
  * choice can be re-measured on the device (environment variable PABI_TILE_VARIANT). */
 /* 1024 threads (64 registers each, 32 warps per SM) in two independent 512-thread groups that share one table
  * image: while one group scans / generates, the other counts.  Measured on startpos perft(8) with the inert-move
- * accounting in place: 2 x 512 parents, pool 9216: 45.8 ms; pool 8192: 46.0; pool 7168: 46.3; 4 x 256 parents,
+ * accounting in place: 2 x 512 parents, pool 9216: 45.8 ms (8960 after the prefix sums of a tile went to 64 bits:
+ * 46.0); pool 8192: 46.0; pool 7168: 46.3; 4 x 256 parents,
  * pool 4608 (the default before): 47.9; 1 x 1024 parents, pool 16384: 47.2; 2 x 448 on 896 threads (72 registers):
  * 47.2; 2 x 384 on 768 threads (80 registers, no spills): 48.8 -- more warps beat more registers */
-using TileDefault = TileConfig<1024, 512, 9216, 1, 2>;
+using TileDefault = TileConfig<1024, 512, 8960, 1, 2>;
 /* small frontiers: shorter tiles, so that every thread group of the grid gets some and the launch lasts a few
  * short tiles instead of one long one (K2 on 2 039 parents: 0.21 -> 0.06 ms) */
 using TileSmall = TileConfig<1024, 64, 4608, 1, 4>;
 using TileTiny = TileConfig<1024, 32, 2048, 1, 4>;
-using TileV1 = TileConfig<1024, 256, 4608, 1, 4>;   /* four 256-parent groups: the default before the inert-move accounting */
+using TileV1 = TileConfig<1024, 256, 4352, 1, 4>;   /* four 256-parent groups: the default before the inert-move accounting */
 using TileV2 = TileConfig<1024, 1024, 16384, 1, 1>; /* one group */
 using TileV3 = TileConfig<1024, 512, 7168, 1, 2>;   /* the default with a smaller pool (more L1) */
 using TileV4 = TileConfig<896, 448, 10240, 1, 2>;   /* 896 threads: 73 registers */

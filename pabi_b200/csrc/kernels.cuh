@@ -85,26 +85,25 @@ __device__ __forceinline__ void group_sync(int group) {
 }
 
 /* Exclusive scan over the THREADS threads of one group (tid = index inside the group). */
-template <int THREADS, int GROUP_THREADS = 0>
-__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* warp_sums /* [THREADS/32 + 1] */, u32& total, int tid_in = -1,
-                                                    int group = 0) {
+template <int THREADS, int GROUP_THREADS = 0, class T = u32>
+__device__ __forceinline__ T block_exclusive_scan(T v, T* warp_sums /* [THREADS/32 + 1] */, T& total, int tid_in = -1, int group = 0) {
   const int tid = tid_in >= 0 ? tid_in : (int)threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  u32 inc = v;
+  T inc = v;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    u32 o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+    T o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
     if (lane >= d) inc += o;
   }
   if (lane == 31) warp_sums[warp] = inc;
   group_sync<GROUP_THREADS>(group);
   if (warp == 0) {
     constexpr int NW = THREADS / 32;
-    u32 w = lane < NW ? warp_sums[lane] : 0;
-    u32 winc = w;
+    T w = lane < NW ? warp_sums[lane] : 0;
+    T winc = w;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      u32 o = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+      T o = __shfl_up_sync(0xFFFFFFFFu, winc, d);
       if (lane >= d) winc += o;
     }
     if (lane < NW) warp_sums[lane] = winc - w;
@@ -112,7 +111,7 @@ __device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* warp_sums /* [TH
   }
   group_sync<GROUP_THREADS>(group);
   total = warp_sums[THREADS / 32];
-  const u32 r = warp_sums[warp] + inc - v;
+  const T r = warp_sums[warp] + inc - v;
   group_sync<GROUP_THREADS>(group); /* warp_sums may be reused by the caller's next scan */
   return r;
 }
@@ -771,13 +770,14 @@ struct TileGroupShared {
   u64 parents[POS_WORDS][CFG::PARENTS];
   u32 pool[CFG::POOL];
   u32 parent_nodes[CFG::PARENTS]; /* K2, multi-root: nodes below each parent */
-  u32 warp_sums[CFG::GROUP_THREADS / 32 + 1];
+  u64 warp_sums[CFG::GROUP_THREADS / 32 + 1];
   unsigned long long next_tile; /* TILE_LEAF: the tile this group took from the ticket counter */
   u64 guard[CFG::PARENTS];      /* TILE_LEAF: TContext::guard of each parent (incremental.cuh) */
   u64 reach[CFG::PARENTS];      /* TILE_LEAF: TContext::reach */
   u64 zone[CFG::PARENTS];       /* TILE_LEAF: TContext::zone */
   u64 active[CFG::PARENTS];     /* TILE_LEAF: SplitCounter::active */
-  u32 offs[CFG::PARENTS + 1];   /* TILE_LEAF: packed exclusive prefix (other << 16 | clean) of the parents' move counts */
+  u64 offs[CFG::PARENTS + 1];   /* TILE_LEAF: packed exclusive prefix (other << 32 | clean) of the parents' move counts: a tile
+                                   of 512 parents can hold more than 65 535 moves of one class */
 };
 
 template <class CFG>
@@ -879,7 +879,7 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
     const size_t i = tile * PARENTS + tid;
     const bool valid = tid < PARENTS && i < n;
     u32 cnt = 0, off = 0, total;
-    u32 clean_total = 0; /* K2: the first clean_total children of the tile take the fast path */
+    u64 cnt2 = 0; /* K2: (other << 32 | clean) pool entries of this parent */
     u32 inert_nodes = 0; /* K2: replies to this parent's inert moves */
     u64 out_base = 0; /* global index of this tile's first child / move */
     if (valid) {
@@ -895,7 +895,7 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         sh.guard[tid] = ctx.guard, sh.reach[tid] = ctx.reach, sh.zone[tid] = ctx.zone;
         SplitCounter counter{ctx.zone};
         enumerate_split(p, tb, ctx.reach, ctx.guard, counter);
-        cnt = counter.other << 16 | counter.clean;
+        cnt2 = (u64)counter.other << 32 | counter.clean;
         sh.active[tid] = counter.active;
         p.meta |= (u64)counter.parts << META_PARTS;
         /* inert moves are settled here: each has ctx.total replies */
@@ -909,10 +909,12 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
     }
     if (LEAF) {
       if (MULTI_ROOT && tid < PARENTS) sh.parent_nodes[tid] = inert_nodes;
-      off = block_exclusive_scan<GT, SYNC>(cnt, sh.warp_sums, total, tid, group); /* both halves: < 2^16 per tile */
-      clean_total = total & 0xFFFF;
-      total = clean_total + (total >> 16);
+      u64 total2;
+      const u64 off2 = block_exclusive_scan<GT, SYNC, u64>(cnt2, sh.warp_sums, total2, tid, group);
+      total = (u32)total2 + (u32)(total2 >> 32);
       if (tid == 0 && total) atomicAdd(out.visited, (unsigned long long)total); /* statistics: positions at the last ply but one */
+      if (tid < PARENTS) sh.offs[tid] = off2;
+      if (tid == 0) sh.offs[PARENTS] = total2;
     } else {
       const size_t tile_first = first + tile * PARENTS;
       const size_t tile_end = first + min((tile + 1) * (size_t)PARENTS, n);
@@ -937,10 +939,8 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
        * size (every thread finds the same boundaries by binary search in the prefix array).  Inside a chunk the
        * clean children come first, the others follow. */
       static_assert(POOL >= 1024, "a chunk leaves room for one more parent's moves");
-      if (tid < PARENTS) sh.offs[tid] = off;
-      if (tid == 0) sh.offs[PARENTS] = (total - clean_total) << 16 | clean_total;
       group_sync<SYNC>(group);
-      const auto entries_before = [&](u32 b) { const u32 v = sh.offs[b]; return (v & 0xFFFF) + (v >> 16); };
+      const auto entries_before = [&](u32 b) { const u64 v = sh.offs[b]; return (u32)v + (u32)(v >> 32); };
       const u32 n_chunks = total <= (u32)POOL ? 1 : (total + (POOL - 256) - 1) / (POOL - 256); /* a parent has < 256 moves */
       u32 a = 0;
       for (u32 j = 1; j <= n_chunks; j++) {
@@ -954,15 +954,16 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
           }
           b = lo_b;
         }
-        const u32 lo = sh.offs[a], hi = sh.offs[b];
-        const u32 clean_base = lo & 0xFFFF, other_base = lo >> 16;
-        const u32 clean_here = (hi & 0xFFFF) - clean_base, end = clean_here + (hi >> 16) - other_base;
+        const u64 lo = sh.offs[a], hi = sh.offs[b];
+        const u32 clean_base = (u32)lo, other_base = (u32)(lo >> 32);
+        const u32 clean_here = (u32)hi - clean_base, end = clean_here + (u32)(hi >> 32) - other_base;
         const u32 chunk_first = a;
         a = b;
         if (end == 0) continue;
-        if (cnt && (u32)tid >= chunk_first && (u32)tid < b) {
-          /* the parent is re-read from shared memory so that it does not occupy registers during phase B */
-          SplitEmitter emit{sh.pool, (off & 0xFFFF) - clean_base, clean_here + (off >> 16) - other_base, (u32)tid << 16, sh.zone[tid]};
+        if ((u32)tid >= chunk_first && (u32)tid < b && sh.offs[tid + 1] != sh.offs[tid]) {
+          /* the parent and its offsets are re-read from shared memory so that they do not occupy registers during phase B */
+          const u64 mine = sh.offs[tid];
+          SplitEmitter emit{sh.pool, (u32)mine - clean_base, clean_here + (u32)(mine >> 32) - other_base, (u32)tid << 16, sh.zone[tid]};
           const Pos p = tile_parent(sh, tid);
           enumerate_split(p, tb, sh.reach[tid], sh.guard[tid], emit, sh.active[tid], (u32)(p.meta >> META_PARTS) & PART_ALL);
         }

@@ -427,6 +427,15 @@ def test_colour_symmetry_at_full_size(pb, engine, vectors):
     assert engine.perft_batch(flipped, 4).tolist() == engine.perft_batch([fen_pos(pb, c["fen"]) for c in big[:4]], 4).tolist()
 
 
+def test_dense_position_large_tiles(pb, engine):
+    """Ten queens a side: ~120 moves per position, almost none of them quiet, so a 512-parent tile of K2 holds about
+    62 000 pool entries of one class -- the per-class prefix sums of a tile must not be 16-bit.  Counts from the oracle."""
+    p = pb.Position.try_from("knq5/ppQ1qQQ1/2q4q/5Q2/1Q1Q3q/2qQ3q/Q4qPP/q1Q3NK w - - 0 1")
+    assert engine.perft(p, 3) == 1_664_938
+    assert engine.perft(p, 4) == 169_711_264
+    assert engine.perft(p, 5) == 19_678_195_927
+
+
 def test_command_line(pb):
     """python -m pabi_b200: the OpenBench line the reference's `openbench()` is meant to print (src/engine/mod.rs:176-190,
     tests/integration.rs:23-34: "<nodes> nodes <nps> nps") over the positions of benches/chess.rs:52-86, and perft divide."""
