@@ -434,6 +434,14 @@ def test_dense_position_large_tiles(pb, engine):
     assert engine.perft(p, 3) == 1_664_938
     assert engine.perft(p, 4) == 169_711_264
     assert engine.perft(p, 5) == 19_678_195_927
+    # the same family through the list kernels: a warp's 32 positions hold ~3 800 moves, twice its shared-memory pool
+    _, ply1 = engine.expand_batch([p])
+    _, ply2 = engine.expand_batch(ply1)
+    offsets, moves = engine.generate_moves_batch(ply2)
+    want_offsets, want_moves = oracle.generate_moves_batch(np.ascontiguousarray(ply2))
+    assert len(ply2) == 13_774 and np.array_equal(offsets, want_offsets) and np.array_equal(moves, want_moves)
+    assert engine.perft_batch(ply2[:700], 2).tolist() == [
+        oracle.perft(oracle.Position.from_buffer_copy(ply2[i].tobytes()), 2) for i in range(700)]
 
 
 def test_command_line(pb):
