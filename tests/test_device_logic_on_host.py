@@ -220,3 +220,22 @@ def test_quiet_move_fast_path_on_playout_positions():
             total += moves
             total_clean += clean
     assert total > 500_000 and 0.05 < total_clean / total < 0.95
+
+
+SPECIAL = [  # positions unlike anything in the reference trees or the playouts: many queens, bare castling rights, promotions
+    "knq5/ppQ1qQQ1/2q4q/5Q2/1Q1Q3q/2qQ3q/Q4qPP/q1Q3NK w - - 0 1",
+    "kn1Q3q/pp5q/4Qq1q/Q3Q3/q2Q2Q1/1QQ2q1Q/q4qPP/qq1Q2NK w - - 0 1",
+    "n1n5/PPPk4/8/8/8/8/4Kppp/5N1N b - - 0 1",
+    "r3k2r/8/8/8/8/8/8/R3K2R w KQkq - 0 1",
+    "4k3/8/8/8/8/8/8/4K2R w K - 0 1",
+    "r3k2r/1b4bq/8/8/8/8/7B/R3K2R w KQkq - 0 1",
+    "8/1n4N1/2k5/8/8/5K2/1N4n1/8 b - - 0 1",
+    "rnbqkb1r/ppppp1pp/7n/4Pp2/8/8/PPPP1PPP/RNBQKBNR w KQkq f6 0 3",
+    "8/5bk1/8/2Pp4/8/1K6/8/8 w - d6 0 1",
+]
+
+
+@pytest.mark.parametrize("fen", SPECIAL)
+def test_quiet_move_fast_path_on_special_positions(fen):
+    parents, moves, clean, mismatches, inert = incremental(oracle.parse(fen), 2)
+    assert mismatches == 0 and parents > 50 and moves >= clean >= inert
