@@ -231,7 +231,7 @@ SPECIAL = [  # positions unlike anything in the reference trees or the playouts:
     "r3k2r/1b4bq/8/8/8/8/7B/R3K2R w KQkq - 0 1",
     "8/1n4N1/2k5/8/8/5K2/1N4n1/8 b - - 0 1",
     "rnbqkb1r/ppppp1pp/7n/4Pp2/8/8/PPPP1PPP/RNBQKBNR w KQkq f6 0 3",
-    "8/5bk1/8/2Pp4/8/1K6/8/8 w - d6 0 1",
+    "8/8/1k6/2b5/2pP4/8/5K2/8 b - d3 0 1",
 ]
 
 
