@@ -819,11 +819,11 @@ PB_HD void make_move(Pos& p, const TB& tb, u16 mv) {
   p.meta = make_meta(castling, ep, us ^ 1, halfmove, fullmove);
 }
 
-/* make_move for the counting path: the moving piece's kind comes with the move, the clocks
- * (halfmove, fullmove: position.rs:419,428-430) are not maintained because a count does not
- * read them.  Board, castling rights, en passant square and side to move are exactly those of
+/* make_move with the moving piece's kind known (it comes with every generated move).  The counting
+ * path does not maintain the clocks (halfmove, fullmove: position.rs:419,428-430) because a count does
+ * not read them; K1 (CLOCKS) does, its children are complete records.  Board, castling rights, en passant square and side to move are exactly those of
  * make_move (checked node by node in tests/test_device_logic_on_host.py). */
-template <int US = -1, bool TRACK_KINGS = false, class TB>
+template <int US = -1, bool TRACK_KINGS = false, bool CLOCKS = false, class TB>
 PB_HD void make_move_kind(Pos& p, const TB& tb, u16 mv, int kind) {
   const int from = mv & 63, to = (mv >> 6) & 63, promo = (mv >> 12) & 7;
   const u64 fb = bit(from), tbit = bit(to), m = fb | tbit;
@@ -832,6 +832,13 @@ PB_HD void make_move_kind(Pos& p, const TB& tb, u16 mv, int kind) {
   const int prev_ep = meta_ep(p.meta);
   int ep = NO_SQUARE;
   u64 white = p.white & ~tbit;
+  /* CLOCKS (K1, whose children are complete records): position.rs:419 and the resets of :470-502 / :504-618 */
+  int halfmove = 0, fullmove = 0;
+  if (CLOCKS) {
+    const bool resets = kind == KIND_PAWN || ((p.pawns | p.knights | p.bishops | p.rooks | p.queens) & tbit) != 0;
+    halfmove = resets ? 0 : (meta_halfmove(p.meta) + 1) & 255;
+    fullmove = (meta_fullmove(p.meta) + us) & 0xFFFF; /* :428-430 */
+  }
   /* handle_capture: whatever stood on `to` (never a king, never ours) is gone */
   p.pawns &= ~tbit, p.knights &= ~tbit, p.bishops &= ~tbit, p.rooks &= ~tbit, p.queens &= ~tbit;
   if (kind == KIND_PAWN) {
@@ -878,7 +885,7 @@ PB_HD void make_move_kind(Pos& p, const TB& tb, u16 mv, int kind) {
     kings_known = p.meta & (0xFFFULL << META_MOVER_KING);
     if (kind == KIND_KING) kings_known = (kings_known & ~(63ULL << META_MOVER_KING)) | ((u64)to << META_MOVER_KING);
   }
-  p.meta = make_meta(castling, ep, us ^ 1, 0, 0) | kings_known;
+  p.meta = make_meta(castling, ep, us ^ 1, halfmove, fullmove) | kings_known;
 }
 
 /* 64-bit key with the equality semantics of the reference's `Position::hash()` AS MAINTAINED BY

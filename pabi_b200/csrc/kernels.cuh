@@ -1003,7 +1003,7 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
           }
           const int parent = (e >> 16) & 0xFFF;
           Pos q = tile_parent(sh, parent);
-          make_move(q, tb, (u16)(e & 0xFFFF));
+          make_move_kind<-1, false, true>(q, tb, (u16)(e & 0xFFFF), (int)(e >> 28)); /* == make_move, without the piece lookup */
           const size_t o = (size_t)(out_base + w + c);
           store_pos(out.children.rec, out.children.stride, o, q);
           if (MULTI_ROOT) out.children.roots[o] = in.roots[first + tile * PARENTS + parent];

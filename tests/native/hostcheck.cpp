@@ -132,9 +132,11 @@ static uint64_t walk_compare(const pabi_position_t& p, int depth, oracle_gen_fn 
     b = unpack_record(c, a.hash);
     Pos ck = r; /* the counting path's make_move: same board, rights, ep square, side to move */
     make_move_kind(ck, tb, want[i], kinds[i]);
+    Pos cc = r; /* K1's make_move: the same with the clocks, i.e. the whole record */
+    make_move_kind<-1, false, true>(cc, tb, want[i], kinds[i]);
     const bool same_kind = ck.white == c.white && ck.pawns == c.pawns && ck.knights == c.knights && ck.bishops == c.bishops &&
                            ck.rooks == c.rooks && ck.queens == c.queens && ck.kings == c.kings &&
-                           (ck.meta & 0xFFFF) == (c.meta & 0xFFFF);
+                           (ck.meta & 0xFFFF) == (c.meta & 0xFFFF) && __builtin_memcmp(&cc, &c, sizeof c) == 0;
     if (__builtin_memcmp(&a, &b, sizeof a) != 0 || !same_kind) {
       if (first_bad) *first_bad = p;
       return bad + 1;
