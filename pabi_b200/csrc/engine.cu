@@ -265,11 +265,21 @@ void launch_leaf(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n) {
 }
 
 /* K1: children of records [first, first + n) of `in`, at the offsets of `prefix` (count_and_scan) */
+template <class CFG>
+void launch_expand_acc(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t first, size_t n, const u64* prefix, const TileOut& out) {
+  if (acc == PER_ROOT) launch_tile_cfg<TILE_EXPAND, PER_ROOT, CFG>(ctx, in, first, n, prefix, out);
+  else if (acc == WEIGHTED) launch_tile_cfg<TILE_EXPAND, WEIGHTED, CFG>(ctx, in, first, n, prefix, out);
+  else launch_tile_cfg<TILE_EXPAND, SINGLE_ROOT, CFG>(ctx, in, first, n, prefix, out);
+}
+
 void launch_expand(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t first, size_t n, const u64* prefix, Frontier children) {
   const TileOut out{children, nullptr, nullptr, nullptr, nullptr, nullptr};
-  if (acc == PER_ROOT) launch_tile_cfg<TILE_EXPAND, PER_ROOT, TileDefault>(ctx, in, first, n, prefix, out);
-  else if (acc == WEIGHTED) launch_tile_cfg<TILE_EXPAND, WEIGHTED, TileDefault>(ctx, in, first, n, prefix, out);
-  else launch_tile_cfg<TILE_EXPAND, SINGLE_ROOT, TileDefault>(ctx, in, first, n, prefix, out);
+  /* small frontiers in shorter tiles, as in launch_leaf: 8 902 parents in 512-parent tiles keep 18 of the 296 thread
+   * groups of the grid busy */
+  const size_t groups = (size_t)ctx->sm_count * TileDefault::GROUPS;
+  if (ctx->tile_variant == 0 && n < groups * TileSmall::PARENTS) launch_expand_acc<TileTiny>(ctx, acc, in, first, n, prefix, out);
+  else if (ctx->tile_variant == 0 && n < groups * TileDefault::PARENTS) launch_expand_acc<TileSmall>(ctx, acc, in, first, n, prefix, out);
+  else launch_expand_acc<TileDefault>(ctx, acc, in, first, n, prefix, out);
 }
 
 /* K3: ordered move lists of records [0, n) at the offsets of `prefix`; the caller has checked the capacity */
