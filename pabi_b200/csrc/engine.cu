@@ -351,8 +351,8 @@ int root_levels(pabi_cuda_ctx* ctx, int lv, size_t& n, int max_plies, Accounting
     alloc_level(ctx, ctx->levels[lv + k], ctx->capacity);
     levels.level[k] = frontier_of(ctx->levels[lv + k]);
   }
-  if (acc == PER_ROOT) k_root_levels<true><<<1, ROOT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, levels, (u32)n, max_plies, ctx->d_result);
-  else k_root_levels<false><<<1, ROOT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, levels, (u32)n, max_plies, ctx->d_result);
+  if (acc == PER_ROOT) k_root_levels<true><<<1, ROOT_THREADS, sizeof(RootShared), ctx->stream>>>(ctx->dt, levels, (u32)n, max_plies, ctx->d_result);
+  else k_root_levels<false><<<1, ROOT_THREADS, sizeof(RootShared), ctx->stream>>>(ctx->dt, levels, (u32)n, max_plies, ctx->d_result);
   LAUNCHED();
   CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result, 3 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -593,8 +593,8 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     CK(cudaMallocHost(&ctx->h_result, 4 * sizeof(u64)));
     /* kernels that stage the table image need more than the default 48 KB of dynamic shared memory */
     CK(cudaFuncSetAttribute(k_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
-    CK(cudaFuncSetAttribute(k_root_levels<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
-    CK(cudaFuncSetAttribute(k_root_levels<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_root_levels<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RootShared)));
+    CK(cudaFuncSetAttribute(k_root_levels<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RootShared)));
     CK(cudaFuncSetAttribute(k_count_accumulate<SINGLE_ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_count_accumulate<PER_ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_count_accumulate<WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));

@@ -559,15 +559,22 @@ k_scan_down(const u32* __restrict__ in, size_t n, const u64* __restrict__ tile_s
  * frontier written, records expanded}. */
 constexpr int ROOT_THREADS = 1024;
 constexpr int ROOT_MAX_PLIES = 8;
+constexpr int ROOT_POOL = 16384; /* moves of one ply that the block makes cooperatively (a fuller ply: one thread per parent) */
 struct RootLevels {
   Frontier level[ROOT_MAX_PLIES + 1];
+};
+struct RootShared {
+  SharedTables tables;
+  u64 parents[POS_WORDS][ROOT_THREADS];
+  u32 pool[ROOT_POOL];
 };
 
 template <bool MULTI_ROOT>
 __global__ void __launch_bounds__(ROOT_THREADS, 1)
 k_root_levels(DeviceTables dt, RootLevels lv, u32 n, int max_plies, u64* __restrict__ result) {
   extern __shared__ __align__(16) unsigned char smem[];
-  SharedTables* sh = reinterpret_cast<SharedTables*>(smem);
+  RootShared& rs = *reinterpret_cast<RootShared*>(smem);
+  SharedTables* sh = &rs.tables;
   stage_tables(sh, dt.image);
   const Tables tb{sh, dt.g};
   __shared__ u32 warp_sums[ROOT_THREADS / 32 + 1];
@@ -581,9 +588,32 @@ k_root_levels(DeviceTables dt, RootLevels lv, u32 n, int max_plies, u64* __restr
     if ((u32)tid < n) {
       p = load_pos(cur.rec, cur.stride, tid);
       cnt = count_moves(p, tb);
+      rs.parents[0][tid] = p.white, rs.parents[1][tid] = p.pawns, rs.parents[2][tid] = p.knights, rs.parents[3][tid] = p.bishops;
+      rs.parents[4][tid] = p.rooks, rs.parents[5][tid] = p.queens, rs.parents[6][tid] = p.kings, rs.parents[7][tid] = p.meta;
     }
     u32 off = block_exclusive_scan<ROOT_THREADS>(cnt, warp_sums, total);
-    if (cnt) {
+    if (total <= (u32)ROOT_POOL) {
+      /* as in K1: the parents write their move lists into the pool, then the whole block makes the moves, one child
+       * per thread and step, with coalesced stores (400 parents -> 8 902 children keep all 1 024 threads busy) */
+      if (cnt) {
+        u32 j = off;
+        generate_moves(p, tb, [&](int from, int to, int promo, int kind) {
+          rs.pool[j++] = ((u32)kind << 28) | ((u32)tid << 16) | pack_move(from, to, promo);
+        });
+      }
+      __syncthreads();
+      for (u32 c = tid; c < total; c += ROOT_THREADS) {
+        const u32 e = rs.pool[c];
+        const int parent = (e >> 16) & 0xFFF;
+        Pos q;
+        q.white = rs.parents[0][parent], q.pawns = rs.parents[1][parent], q.knights = rs.parents[2][parent];
+        q.bishops = rs.parents[3][parent], q.rooks = rs.parents[4][parent], q.queens = rs.parents[5][parent];
+        q.kings = rs.parents[6][parent], q.meta = rs.parents[7][parent];
+        make_move_kind<-1, false, true>(q, tb, (u16)(e & 0xFFFF), (int)(e >> 28));
+        store_pos(next.rec, next.stride, c, q);
+        if (MULTI_ROOT) next.roots[c] = cur.roots[parent];
+      }
+    } else if (cnt) {
       const u32 root = MULTI_ROOT ? cur.roots[tid] : 0;
       generate_moves(p, tb, [&](int from, int to, int promo, int) {
         Pos q = p;
