@@ -404,12 +404,22 @@ void descend(pabi_cuda_ctx* ctx, int lv, size_t n, int remaining, Accounting acc
     /* levels may have been swapped by a deeper merge_transpositions: re-read them every time */
     Level& cur = ctx->levels[lv];
     Level& next = ctx->levels[lv + 1];
-    k_chunk_end<<<1, 1, 0, ctx->stream>>>(cur.prefix, start, n, (u64)next.cap, ctx->d_result);
-    LAUNCHED();
-    CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result, 2 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    const size_t end = (size_t)ctx->h_result[0];
-    size_t children = (size_t)ctx->h_result[1];
+    size_t end = n, children = 0;
+    bool whole = false;
+    if (start == 0) { /* the usual case, all children fit the next level: the total is the last prefix entry, no search */
+      CK(cudaMemcpyAsync(ctx->h_result, cur.prefix + n, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      children = (size_t)ctx->h_result[0];
+      whole = children <= next.cap;
+    }
+    if (!whole) {
+      k_chunk_end<<<1, 1, 0, ctx->stream>>>(cur.prefix, start, n, (u64)next.cap, ctx->d_result);
+      LAUNCHED();
+      CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result, 2 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      end = (size_t)ctx->h_result[0];
+      children = (size_t)ctx->h_result[1];
+    }
     if (end == start) {
       ctx->error = "frontier capacity is smaller than one position's move list";
       throw CudaFail{cudaErrorInvalidValue};
