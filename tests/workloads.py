@@ -38,15 +38,16 @@ def chess324_synth_book() -> np.ndarray:
     return np.ascontiguousarray(np.concatenate(chunks))
 
 
-def playout_positions(target: int) -> np.ndarray:
+def playout_positions(target: int, seed: int = 0x5EED0000) -> np.ndarray:
     """Config #5: positions of seeded random playouts from the start position (even games) or a
-    Chess324 array (odd games), every position recorded, games capped at 200 plies."""
+    Chess324 array (odd games), every position recorded, games capped at 200 plies.  `seed` is the
+    documented one of SURVEY.md 8(d) unless a tool asks for other games."""
     fens = chess324_fens()
     chunks, total, g = [], 0, 0
     start = oracle.starting()
     while total < target:
         root = start if g % 2 == 0 else oracle.parse(fens[(g // 2) % 324])
-        arr = oracle.random_playout(root, 0x5EED0000 + g, 200)
+        arr = oracle.random_playout(root, seed + g, 200)
         chunks.append(arr)
         total += len(arr)
         g += 1

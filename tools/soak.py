@@ -1,4 +1,5 @@
 """One-off differential soak on cuda:0 (not part of pytest): large random samples, CUDA path vs oracle.
+Usage: python tools/soak.py [positions [seed]]   (default 3 000 000 positions of the documented seed)
 
   - 3M playout positions (startpos + all Chess324 arrays): ordered move lists, counts, in_check
   - 200k of them: perft(3) per root
@@ -21,7 +22,9 @@ import pabi_b200 as pb  # noqa: E402
 
 e = pb.Engine(0)
 t0 = time.time()
-positions = workloads.playout_positions(3_000_000)
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 3_000_000
+SEED = int(sys.argv[2], 0) if len(sys.argv) > 2 else 0x5EED0000
+positions = workloads.playout_positions(N, SEED)
 print(f"{len(positions)} positions generated in {time.time() - t0:.1f}s", flush=True)
 off, mv = e.generate_moves_batch(positions)
 woff, wmv = oracle.generate_moves_batch(positions)
