@@ -167,16 +167,16 @@ constexpr size_t FLAT_SMEM = sizeof(SharedTables);
  * 46.0); pool 8192: 46.0; pool 7168: 46.3; 4 x 256 parents,
  * pool 4608 (the default before): 47.9; 1 x 1024 parents, pool 16384: 47.2; 2 x 448 on 896 threads (72 registers):
  * 47.2; 2 x 384 on 768 threads (80 registers, no spills): 48.8 -- more warps beat more registers */
-using TileDefault = TileConfig<1024, 512, 8960, 1, 2>;
+using TileDefault = TileConfig<1024, 512, 14080, 1, 2>;
 /* small frontiers: shorter tiles, so that every thread group of the grid gets some and the launch lasts a few
  * short tiles instead of one long one (K2 on 2 039 parents: 0.21 -> 0.06 ms) */
-using TileSmall = TileConfig<1024, 64, 4608, 1, 4>;
-using TileTiny = TileConfig<1024, 32, 2048, 1, 4>;
-using TileV1 = TileConfig<1024, 256, 4352, 1, 4>;   /* four 256-parent groups: the default before the inert-move accounting */
-using TileV2 = TileConfig<1024, 1024, 16384, 1, 1>; /* one group */
-using TileV3 = TileConfig<1024, 512, 7168, 1, 2>;   /* the default with a smaller pool (more L1) */
-using TileV4 = TileConfig<896, 448, 10240, 1, 2>;   /* 896 threads: 73 registers */
-using TileV5 = TileConfig<768, 384, 12288, 1, 2>;   /* 768 threads: 85 registers, no spills */
+using TileSmall = TileConfig<1024, 64, 5120, 1, 4>;
+using TileTiny = TileConfig<1024, 32, 2304, 1, 4>;
+using TileV1 = TileConfig<1024, 256, 7040, 1, 4>;   /* four 256-parent groups: the default before the inert-move accounting */
+using TileV2 = TileConfig<1024, 1024, 28160, 1, 1>; /* one group */
+using TileV3 = TileConfig<1024, 512, 10240, 1, 2>;   /* the default with a smaller pool (more L1) */
+using TileV4 = TileConfig<896, 448, 15104, 1, 2>;   /* 896 threads: 73 registers */
+using TileV5 = TileConfig<768, 384, 16128, 1, 2>;   /* 768 threads: 85 registers, no spills */
 constexpr int TILE_VARIANTS = 6;
 
 /* prefix[0..n] = exclusive scan of counts[0..n) */

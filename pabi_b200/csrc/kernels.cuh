@@ -802,12 +802,8 @@ struct TileGroupShared {
   u32 parent_nodes[CFG::PARENTS]; /* K2, multi-root: nodes below each parent */
   u64 warp_sums[CFG::GROUP_THREADS / 32 + 1];
   unsigned long long next_tile; /* TILE_LEAF: the tile this group took from the ticket counter */
-  u64 guard[CFG::PARENTS];      /* TILE_LEAF: TContext::guard of each parent (incremental.cuh) */
-  u64 reach[CFG::PARENTS];      /* TILE_LEAF: TContext::reach */
-  u64 zone[CFG::PARENTS];       /* TILE_LEAF: TContext::zone */
-  u64 active[CFG::PARENTS];     /* TILE_LEAF: SplitCounter::active */
-  u64 offs[CFG::PARENTS + 1];   /* TILE_LEAF: packed exclusive prefix (other << 32 | clean) of the parents' move counts: a tile
-                                   of 512 parents can hold more than 65 535 moves of one class */
+  u32 cursor;                   /* TILE_LEAF: pool entries reserved so far, other << 16 | clean (DirectEmitter) */
+  u32 overflow;                 /* TILE_LEAF: a reservation did not fit: the range of parents is halved and redone */
 };
 
 template <class CFG>
@@ -840,40 +836,74 @@ struct TileOut {
   unsigned long long* ticket;       /* TILE_LEAF: tiles are handed out dynamically (zeroed before the launch) */
 };
 
-/* enumerate_split sink of K2's phase A: clean moves go to pool[clean_at ...), the others to
- * pool[other_at ...); the chunk was sized so that everything fits */
-struct SplitEmitter {
+/* enumerate_split sink of K2 when every parent enumerates its moves ONCE: the slots of a piece's entries are reserved
+ * with one shared-memory atomic on a packed cursor (clean entries grow from the front of the pool, the others from its
+ * end), the inert moves are counted.  A reservation that does not fit raises `overflow`; the kernel then redoes the range
+ * of parents in halves. */
+struct DirectEmitter {
   u32* pool;
-  u32 clean_at, other_at, tag; /* tag = parent << 16 */
-  u64 zone;                    /* inert moves (incremental.cuh) were accounted for in the sizing pass */
+  u32* cursor;
+  u32* overflow;
+  u32 cap, tag; /* tag = parent << 16 */
+  u64 zone;
+  u32 inert = 0;
+  __device__ __forceinline__ bool reserve(u32 n_clean, u32 n_other, u32& clean_at, u32& other_at) {
+    const u32 old = atomicAdd(cursor, n_clean | (n_other << 16));
+    const u32 c0 = old & 0xFFFF, o0 = old >> 16;
+    if (c0 + n_clean + o0 + n_other > cap) {
+      *overflow = 1;
+      return false;
+    }
+    clean_at = c0, other_at = cap - o0 - n_other;
+    return true;
+  }
   __device__ __forceinline__ void put(u32& at, int from, int to, int promo, int kind) {
     pool[at++] = ((u32)kind << 28) | tag | pack_move(from, to, promo);
   }
-  __device__ __forceinline__ void other(int from, int to, int kind) {
+  __device__ __forceinline__ void other(u32& at, int from, int to, int kind) {
     if (kind == KIND_PAWN && to < 8) { /* black promotes on rank 1 */
-      put(other_at, from, to, PROMO_Q, kind), put(other_at, from, to, PROMO_R, kind);
-      put(other_at, from, to, PROMO_B, kind), put(other_at, from, to, PROMO_N, kind);
+      put(at, from, to, PROMO_Q, kind), put(at, from, to, PROMO_R, kind);
+      put(at, from, to, PROMO_B, kind), put(at, from, to, PROMO_N, kind);
     } else {
-      put(other_at, from, to, 0, kind);
+      put(at, from, to, 0, kind);
     }
   }
   __device__ __forceinline__ void piece(int from, int kind, u64 c, u64 o) {
-    for (Squares t(c & ~inert_targets(zone, from, c)); t.any();) put(clean_at, from, t.pop(), 0, kind);
+    const u64 rest = c & ~inert_targets(zone, from, c);
+    inert += popc(c ^ rest);
+    if ((rest | o) == 0) return;
+    u32 clean_at, other_at;
+    if (!reserve(popc(rest), popc(o), clean_at, other_at)) return;
+    for (Squares t(rest); t.any();) put(clean_at, from, t.pop(), 0, kind);
     for (Squares t(o); t.any();) put(other_at, from, t.pop(), 0, kind);
   }
   __device__ __forceinline__ void pushes(u64 c, u64 o, int delta) {
-    for (Squares t(c & ~inert_pushes(zone, c, delta)); t.any();) {
+    const u64 rest = c & ~inert_pushes(zone, c, delta);
+    inert += popc(c ^ rest);
+    if ((rest | o) == 0) return;
+    u32 clean_at, other_at;
+    if (!reserve(popc(rest), popc(o) + 3 * popc(o & RANK_1), clean_at, other_at)) return;
+    for (Squares t(rest); t.any();) {
       const int to = t.pop();
       put(clean_at, to + delta, to, 0, KIND_PAWN);
     }
     for (Squares t(o); t.any();) {
       const int to = t.pop();
-      other(to + delta, to, KIND_PAWN);
+      other(other_at, to + delta, to, KIND_PAWN);
     }
   }
-  __device__ __forceinline__ void pawn_capture(int from, int to) { other(from, to, KIND_PAWN); }
-  __device__ __forceinline__ void en_passant(int from, int to) { put(other_at, from, to, 0, KIND_PAWN); }
-  __device__ __forceinline__ void castle(int from, int to) { put(other_at, from, to, 0, KIND_KING); }
+  __device__ __forceinline__ void pawn_capture(int from, int to) {
+    u32 clean_at, other_at;
+    if (reserve(0, to < 8 ? 4 : 1, clean_at, other_at)) other(other_at, from, to, KIND_PAWN);
+  }
+  __device__ __forceinline__ void en_passant(int from, int to) {
+    u32 clean_at, other_at;
+    if (reserve(0, 1, clean_at, other_at)) put(other_at, from, to, 0, KIND_PAWN);
+  }
+  __device__ __forceinline__ void castle(int from, int to) {
+    u32 clean_at, other_at;
+    if (reserve(0, 1, clean_at, other_at)) put(other_at, from, to, 0, KIND_KING);
+  }
 };
 
 /* In TILE_EXPAND / TILE_MOVES the per-parent counts come from the global scan (`prefix`, built by
@@ -908,44 +938,77 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
     if (tile >= n_tiles) break;
     const size_t i = tile * PARENTS + tid;
     const bool valid = tid < PARENTS && i < n;
+    if (LEAF) {
+      /* Every parent enumerates its moves once: context, split, inert moves counted, the rest written straight into
+       * the pool at slots reserved with a shared atomic (DirectEmitter).  The parents of a tile are taken in ranges
+       * [lo, lo + len); a range whose entries do not fit the pool is halved and redone (a single parent always fits). */
+      static_assert(POOL >= 1024 && POOL <= 32768, "one parent's moves fit; the packed cursor has 16 bits per class");
+      const u32 tile_parents = (u32)min((size_t)PARENTS, n - tile * PARENTS);
+      u32 lo = 0, len = PARENTS;
+      while (lo < tile_parents) {
+        if (tid == 0) sh.cursor = 0, sh.overflow = 0;
+        group_sync<SYNC>(group);
+        const bool mine = valid && (u32)tid >= lo && (u32)tid < lo + len;
+        u32 inert_nodes = 0, inert_moves = 0;
+        if (mine) {
+          Pos p = load_pos(in.rec, in.stride, first + i);
+          if (meta_stm(p.meta) == 0) p = mirror(p);
+          const TContext ctx = t_context(p, tb);
+          p.meta = (with_king_squares(p) & ~(0xFFFFULL << META_BASE)) | ((u64)ctx.base << META_BASE);
+          sh.parents[0][tid] = p.white, sh.parents[1][tid] = p.pawns, sh.parents[2][tid] = p.knights;
+          sh.parents[3][tid] = p.bishops, sh.parents[4][tid] = p.rooks, sh.parents[5][tid] = p.queens;
+          sh.parents[6][tid] = p.kings, sh.parents[7][tid] = p.meta;
+          DirectEmitter emit{sh.pool, &sh.cursor, &sh.overflow, (u32)POOL, (u32)tid << 16, ctx.zone};
+          enumerate_split(p, tb, ctx.reach, ctx.guard, emit);
+          inert_moves = emit.inert;
+          inert_nodes = emit.inert * ctx.total;
+        }
+        group_sync<SYNC>(group);
+        if (sh.overflow) { /* the same for every thread of the group: read after the barrier, reset after the next one */
+          len = len > 1 ? len >> 1 : 1;
+          group_sync<SYNC>(group);
+          continue;
+        }
+        inert_children += inert_moves;
+        if (MULTI_ROOT) { if (mine) sh.parent_nodes[tid] = inert_nodes; }
+        else if (mine) acc += ACC == WEIGHTED ? (u64)inert_nodes * in.mult[first + i] : (u64)inert_nodes;
+        const u32 cursor = sh.cursor;
+        const u32 clean_here = cursor & 0xFFFF, others = cursor >> 16, end = clean_here + others;
+        if (tid == 0 && end) atomicAdd(out.visited, (unsigned long long)end); /* statistics: positions at the last ply but one */
+        if (MULTI_ROOT) group_sync<SYNC>(group); /* the per-parent counters are set */
+        for (u32 c = tid; c < end; c += GT) {
+          const u32 e = sh.pool[c < clean_here ? c : POOL - others + (c - clean_here)];
+          const int parent = (e >> 16) & 0xFFF;
+          Pos q = tile_parent(sh, parent);
+          u32 k;
+          if (c < clean_here) { /* quiet move off every line that matters: replies = base + pawns + king */
+            k = count_child_fast(q, tb, (int)(e & 63), (int)((e >> 6) & 63), (int)(e >> 28));
+          } else {
+            make_move_kind<1, true>(q, tb, (u16)(e & 0xFFFF), (int)(e >> 28));
+            k = count_child_white(q, tb);
+          }
+          if (MULTI_ROOT) atomicAdd(&sh.parent_nodes[parent], k);
+          else acc += ACC == WEIGHTED ? k * in.mult[first + tile * PARENTS + parent] : (u64)k;
+        }
+        if (MULTI_ROOT) {
+          group_sync<SYNC>(group);
+          if (mine && sh.parent_nodes[tid]) atomicAdd(out.nodes + in.roots[first + i], (unsigned long long)sh.parent_nodes[tid]);
+        }
+        group_sync<SYNC>(group); /* the pool and the cursor are free again */
+        lo += len;
+      }
+      continue;
+    }
+    /* K1 / K3 */
     u32 cnt = 0, off = 0, total;
-    u64 cnt2 = 0; /* K2: (other << 32 | clean) pool entries of this parent */
-    u32 inert_nodes = 0; /* K2: replies to this parent's inert moves */
     u64 out_base = 0; /* global index of this tile's first child / move */
     if (valid) {
-      Pos p = load_pos(in.rec, in.stride, first + i);
-      if (LEAF) {
-        /* K2 keeps the parent with BLACK to move (mirrored if necessary): every child is then "white
-         * to move", which is what count_moves_white wants, and the mover's colour is a constant.  The
-         * record also carries the king squares and the per-parent context of the quiet-move fast path;
-         * cnt packs (other << 16 | clean) move counts for one scan. */
-        if (meta_stm(p.meta) == 0) p = mirror(p);
-        const TContext ctx = t_context(p, tb);
-        p.meta = (with_king_squares(p) & ~(0xFFFFULL << META_BASE) & ~(0xFFULL << META_PARTS)) | ((u64)ctx.base << META_BASE);
-        sh.guard[tid] = ctx.guard, sh.reach[tid] = ctx.reach, sh.zone[tid] = ctx.zone;
-        SplitCounter counter{ctx.zone};
-        enumerate_split(p, tb, ctx.reach, ctx.guard, counter);
-        cnt2 = (u64)counter.other << 32 | counter.clean;
-        sh.active[tid] = counter.active;
-        p.meta |= (u64)counter.parts << META_PARTS;
-        /* inert moves are settled here: each has ctx.total replies */
-        inert_children += counter.inert;
-        inert_nodes = counter.inert * ctx.total;
-        if (!MULTI_ROOT) acc += ACC == WEIGHTED ? (u64)inert_nodes * in.mult[first + i] : (u64)inert_nodes;
-      }
+      const Pos p = load_pos(in.rec, in.stride, first + i);
       sh.parents[0][tid] = p.white, sh.parents[1][tid] = p.pawns, sh.parents[2][tid] = p.knights;
       sh.parents[3][tid] = p.bishops, sh.parents[4][tid] = p.rooks, sh.parents[5][tid] = p.queens;
       sh.parents[6][tid] = p.kings, sh.parents[7][tid] = p.meta;
     }
-    if (LEAF) {
-      if (MULTI_ROOT && tid < PARENTS) sh.parent_nodes[tid] = inert_nodes;
-      u64 total2;
-      const u64 off2 = block_exclusive_scan<GT, SYNC, u64>(cnt2, sh.warp_sums, total2, tid, group);
-      total = (u32)total2 + (u32)(total2 >> 32);
-      if (tid == 0 && total) atomicAdd(out.visited, (unsigned long long)total); /* statistics: positions at the last ply but one */
-      if (tid < PARENTS) sh.offs[tid] = off2;
-      if (tid == 0) sh.offs[PARENTS] = total2;
-    } else {
+    {
       const size_t tile_first = first + tile * PARENTS;
       const size_t tile_end = first + min((tile + 1) * (size_t)PARENTS, n);
       const u64 tile_prefix = prefix[tile_first];
@@ -963,58 +1026,7 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
       group_sync<SYNC>(group); /* the parents are in shared memory */
     }
 
-    if (LEAF) {
-      /* The pool is filled once per CHUNK of consecutive parents, so that every parent enumerates its moves
-       * exactly once.  A tile whose entries do not fit is cut into the smallest number of chunks of about equal
-       * size (every thread finds the same boundaries by binary search in the prefix array).  Inside a chunk the
-       * clean children come first, the others follow. */
-      static_assert(POOL >= 1024, "a chunk leaves room for one more parent's moves");
-      group_sync<SYNC>(group);
-      const auto entries_before = [&](u32 b) { const u64 v = sh.offs[b]; return (u32)v + (u32)(v >> 32); };
-      const u32 n_chunks = total <= (u32)POOL ? 1 : (total + (POOL - 256) - 1) / (POOL - 256); /* a parent has < 256 moves */
-      u32 a = 0;
-      for (u32 j = 1; j <= n_chunks; j++) {
-        u32 b = PARENTS; /* chunk j: the parents [a, b) whose entries end within the first j / n_chunks of the tile's */
-        if (j < n_chunks) {
-          const u32 limit = (u32)(((u64)total * j) / n_chunks);
-          u32 lo_b = a, hi_b = PARENTS; /* largest b with entries_before(b) <= limit */
-          while (lo_b < hi_b) {
-            const u32 mid = (lo_b + hi_b + 1) >> 1;
-            if (entries_before(mid) <= limit) lo_b = mid; else hi_b = mid - 1;
-          }
-          b = lo_b;
-        }
-        const u64 lo = sh.offs[a], hi = sh.offs[b];
-        const u32 clean_base = (u32)lo, other_base = (u32)(lo >> 32);
-        const u32 clean_here = (u32)hi - clean_base, end = clean_here + (u32)(hi >> 32) - other_base;
-        const u32 chunk_first = a;
-        a = b;
-        if (end == 0) continue;
-        if ((u32)tid >= chunk_first && (u32)tid < b && sh.offs[tid + 1] != sh.offs[tid]) {
-          /* the parent and its offsets are re-read from shared memory so that they do not occupy registers during phase B */
-          const u64 mine = sh.offs[tid];
-          SplitEmitter emit{sh.pool, (u32)mine - clean_base, clean_here + (u32)(mine >> 32) - other_base, (u32)tid << 16, sh.zone[tid]};
-          const Pos p = tile_parent(sh, tid);
-          enumerate_split(p, tb, sh.reach[tid], sh.guard[tid], emit, sh.active[tid], (u32)(p.meta >> META_PARTS) & PART_ALL);
-        }
-        group_sync<SYNC>(group);
-        for (u32 c = tid; c < end; c += GT) {
-          const u32 e = sh.pool[c];
-          const int parent = (e >> 16) & 0xFFF;
-          Pos q = tile_parent(sh, parent);
-          u32 k;
-          if (c < clean_here) { /* quiet move off every line that matters: replies = base + pawns + king */
-            k = count_child_fast(q, tb, (int)(e & 63), (int)((e >> 6) & 63), (int)(e >> 28));
-          } else {
-            make_move_kind<1, true>(q, tb, (u16)(e & 0xFFFF), (int)(e >> 28));
-            k = count_child_white(q, tb);
-          }
-          if (MULTI_ROOT) atomicAdd(&sh.parent_nodes[parent], k);
-          else acc += ACC == WEIGHTED ? k * in.mult[first + tile * PARENTS + parent] : (u64)k;
-        }
-        group_sync<SYNC>(group);
-      }
-    } else {
+    {
       for (u32 w = 0; w < total; w += POOL) { /* sliding windows over the tile's children */
         if (cnt && off < w + POOL && off + cnt > w) {
           u32 j = off;
@@ -1041,10 +1053,6 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         }
         group_sync<SYNC>(group);
       }
-    }
-    if (LEAF && MULTI_ROOT) {
-      if (valid && sh.parent_nodes[tid]) atomicAdd(out.nodes + in.roots[first + i], (unsigned long long)sh.parent_nodes[tid]);
-      group_sync<SYNC>(group);
     }
   }
   if (LEAF) { /* statistics: the inert children were visited too */
