@@ -162,11 +162,11 @@ constexpr size_t FLAT_SMEM = sizeof(SharedTables);
 /* Tile-kernel geometries.  Variant 0 is the default; the others exist so that the
  * choice can be re-measured on the device (environment variable PABI_TILE_VARIANT). */
 /* 1024 threads (64 registers each, 32 warps per SM) in two independent 512-thread groups that share one table
- * image: while one group scans / generates, the other counts.  Measured on startpos perft(8) with the inert-move
- * accounting in place: 2 x 512 parents, pool 9216: 45.8 ms (8960 after the prefix sums of a tile went to 64 bits:
- * 46.0); pool 8192: 46.0; pool 7168: 46.3; 4 x 256 parents,
- * pool 4608 (the default before): 47.9; 1 x 1024 parents, pool 16384: 47.2; 2 x 448 on 896 threads (72 registers):
- * 47.2; 2 x 384 on 768 threads (80 registers, no spills): 48.8 -- more warps beat more registers */
+ * image: while one group generates, the other counts.  The pool takes what is left of the 227 KB of shared memory
+ * after the table image and the parents.  Measured on startpos perft(8) with one enumeration per parent (DirectEmitter):
+ * 2 x 512 parents, pool 14080: 41.4 ms; pool 10240: 41.7; 4 x 256 parents, pool 7040: 41.6; 1 x 1024 parents, pool
+ * 28160: 42.2; 2 x 448 on 896 threads (72 registers): 42.3; 2 x 384 on 768 threads (80 registers): 44.2 -- more warps
+ * beat more registers.  (With two enumerations per parent and a 8960-entry pool the same geometry took 46.0 ms.) */
 using TileDefault = TileConfig<1024, 512, 14080, 1, 2>;
 /* small frontiers: shorter tiles, so that every thread group of the grid gets some and the launch lasts a few
  * short tiles instead of one long one (K2 on 2 039 parents: 0.21 -> 0.06 ms) */

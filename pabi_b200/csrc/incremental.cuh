@@ -26,7 +26,6 @@ namespace pabi {
 /* per-parent context, carried in the shared-memory parent record: `base` in meta bits 32-47 (the
  * fullmove counter is not needed in K2), `guard` in a side array */
 constexpr int META_BASE = 32;
-constexpr int META_PARTS = 16; /* SplitParts of the parent, in the (unused) halfmove field */
 
 struct TContext {
   u64 reach; /* union of T's slider attack sets plus the pieces that shield T's king from an S slider: a clean move
@@ -180,15 +179,10 @@ PB_HD TContext t_context(const Pos& n, const TB& tb) {
  *   en_passant(from, to)
  *   castle(from, to)
  * The union of everything reported is exactly generate_moves(n). */
-enum SplitParts : u32 { PART_PUSH = 1, PART_DOUBLE_PUSH = 2, PART_PAWN_CAPTURE = 4, PART_EN_PASSANT = 8, PART_CASTLE = 16, PART_ALL = 31 };
-
-/* `active` / `parts` restrict the enumeration to the pieces (by from-square) and pawn / castling parts that
- * the sizing pass found to have moves that need a pool entry (SplitCounter::active, ::parts): the emitting
- * pass of K2 then skips every piece whose moves are all inert. */
 template <class TB, class Sink>
-PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 reach, u64 guard, Sink& sink, u64 active = ~0ULL, u32 parts = PART_ALL) {
+PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 reach, u64 guard, Sink& sink) {
   Analysis a;
-  analyze<1>(n, tb, a, (n.kings & ~n.white & active) != 0 || (parts & PART_CASTLE));
+  analyze<1>(n, tb, a);
   const u64 W = a.their;
   const u64 tk_bb = n.kings & W;
   const int tk = lsb(tk_bb);
@@ -196,13 +190,13 @@ PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 reach, u64 guard, Sin
    * outside `reach` (arriving on a king ray they change neither checks nor pins) */
   const u64 open = ~guard & ~W;
   const u64 open_leaper = ~reach & ~W;
-  if ((active >> a.king) & 1) {
+  {
     const u64 c = (reach >> a.king) & 1 ? 0 : a.safe_king & open_leaper;
     sink.piece(a.king, KIND_KING, c, a.safe_king & ~c);
   }
   if (a.block == 0) return;
   const u64 targets = ~a.our & a.block;
-  const u64 movers = a.our & active;
+  const u64 movers = a.our;
   const u64 orth_movers = (n.rooks | n.queens) & movers & orth_neighbours(~a.our); /* hemmed-in sliders have no moves */
   const u64 diag_movers = (n.bishops | n.queens) & movers & diag_neighbours(~a.our);
 
@@ -228,9 +222,9 @@ PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 reach, u64 guard, Sin
   }
 
   /* pawns of the mover (black, moving down the board) */
-  if (parts & (PART_PUSH | PART_DOUBLE_PUSH | PART_PAWN_CAPTURE)) {
+  {
     const PawnSets ps = pawn_sources(n, tb, a);
-    if (parts & PART_PAWN_CAPTURE) {
+    {
       const u64 capture_targets = W & a.block;
       const u64 west_sources = ps.west & (capture_targets << 9) & ~FILE_A; /* black captures towards file a: from - 9 */
       const u64 east_sources = ps.east & (capture_targets << 7) & ~FILE_H; /* towards file h: from - 7 */
@@ -241,7 +235,7 @@ PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 reach, u64 guard, Sin
         for (Squares ts(t); ts.any();) sink.pawn_capture(from, ts.pop());
       }
     }
-    if (parts & (PART_PUSH | PART_DOUBLE_PUSH)) {
+    {
       const u64 empty = ~a.occ;
       const u64 single_all = (ps.pushers >> 8) & empty;
       const u64 single = single_all & a.block;
@@ -251,44 +245,39 @@ PB_HD void enumerate_split(const Pos& n, const TB& tb, u64 reach, u64 guard, Sin
       const u64 beside_t_pawn = ((t_pawns & ~FILE_A) >> 1) | ((t_pawns & ~FILE_H) << 1); /* a double push there creates an en passant square */
       const u64 c1 = single & open_leaper & ~(reach >> 8) & ~RANK_1 & ~checks;
       const u64 c2 = dbl & open_leaper & ~(reach >> 16) & ~checks & ~beside_t_pawn;
-      if (parts & PART_PUSH) sink.pushes(c1, single & ~c1, 8);
-      if (parts & PART_DOUBLE_PUSH) sink.pushes(c2, dbl & ~c2, 16);
+      sink.pushes(c1, single & ~c1, 8);
+      sink.pushes(c2, dbl & ~c2, 16);
     }
   }
-  if ((parts & PART_EN_PASSANT) && meta_ep(n.meta) < NO_SQUARE)
+  if (meta_ep(n.meta) < NO_SQUARE)
     for (Squares b(en_passant_sources(n, tb, a)); b.any();) sink.en_passant(b.pop(), meta_ep(n.meta));
-  if (parts & PART_CASTLE) {
+  {
     const int c = castle_moves(n, a);
     if (c & 1) sink.castle(60, 62);
     if (c & 2) sink.castle(60, 58);
   }
 }
 
-/* (clean, other, inert) move counts of a parent: the sizing pass of the split pool.  Inert moves (clean and
- * off the parent's zone) are never materialised: each of them has TContext::total replies. */
+/* Inert moves (clean and off the parent's zone) are never materialised: each of them has TContext::total replies. */
 PB_HD u64 inert_targets(u64 zone, int from, u64 clean) { return (zone >> from) & 1 ? 0 : clean & ~zone; }
 PB_HD u64 inert_pushes(u64 zone, u64 clean, int delta) { return clean & ~zone & ~(zone >> delta); } /* from = to + delta */
 
+/* (clean, other, inert) move counts of a parent: what K2's DirectEmitter (kernels.cuh) reserves in the pool and what it
+ * settles on the spot.  Host-side reference for the tests (tests/native/hostcheck.cpp). */
 struct SplitCounter {
   u64 zone;
   u32 clean = 0, other = 0, inert = 0;
-  u64 active = 0; /* from-squares of the pieces with a move that needs a pool entry */
-  u32 parts = 0;  /* SplitParts with such a move */
   PB_HD void piece(int from, int, u64 c, u64 o) {
-    const u64 in = inert_targets(zone, from, c);
-    const u32 i = popc(in);
+    const u32 i = popc(inert_targets(zone, from, c));
     inert += i, clean += popc(c) - i, other += popc(o);
-    if ((c ^ in) | o) active |= bit(from);
   }
   PB_HD void pushes(u64 c, u64 o, int delta) {
-    const u64 in = inert_pushes(zone, c, delta);
-    const u32 i = popc(in);
+    const u32 i = popc(inert_pushes(zone, c, delta));
     inert += i, clean += popc(c) - i, other += popc(o) + 3 * popc(o & RANK_1);
-    if ((c ^ in) | o) parts |= delta == 8 ? PART_PUSH : PART_DOUBLE_PUSH;
   }
-  PB_HD void pawn_capture(int, int to) { other += to < 8 ? 4 : 1, parts |= PART_PAWN_CAPTURE; }
-  PB_HD void en_passant(int, int) { ++other, parts |= PART_EN_PASSANT; }
-  PB_HD void castle(int, int) { ++other, parts |= PART_CASTLE; }
+  PB_HD void pawn_capture(int, int to) { other += to < 8 ? 4 : 1; }
+  PB_HD void en_passant(int, int) { ++other; }
+  PB_HD void castle(int, int) { ++other; }
 };
 
 /* Replies to a clean move: n = the normalised parent (black to move; meta carries base and both king

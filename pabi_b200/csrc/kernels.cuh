@@ -768,15 +768,15 @@ __global__ void k_dedup_compact(const u64* __restrict__ rec, size_t stride, size
 
 /* ---- K1 / K2: tile kernels ------------------------------------------------
  * A thread group takes PARENTS consecutive parents at a time:
- *   A0  threads 0..PARENTS-1 size their parent's move list; group exclusive scan.
- *       K1 / K3 read the sizes from the global scan (k_count + k_scan_*).
- *       K2 computes them itself with enumerate_split (incremental.cuh), which also
- *       settles the parent's INERT moves on the spot (replies = inert x total) and
- *       splits the rest into clean and other
- *   A   the same threads write their parent's moves into the shared pool at the scanned
- *       offset, as (kind << 28 | parent << 16 | move); K2: clean entries from the front,
- *       the others behind them, a tile that does not fit in equal chunks of parents;
- *       K1 / K3: reference order, sliding windows
+ *   A   threads 0..PARENTS-1 write their parent's moves into the group's shared-memory pool as
+ *       (kind << 28 | parent << 16 | move).
+ *         K1 / K3: at the offsets of the global scan (k_count + k_scan_*), reference order,
+ *             sliding windows when a tile has more moves than the pool
+ *         K2: one enumeration per parent (enumerate_split, incremental.cuh): the INERT moves
+ *             are settled on the spot (replies = inert x total), the slots of the clean and the
+ *             other moves are reserved with a shared-memory atomic per piece (DirectEmitter):
+ *             clean entries from the front of the pool, the others from its end; a range of
+ *             parents that does not fit is halved and redone
  *   B   every thread takes entries from the pool, parent record from shared memory:
  *         K1: make_move in registers, store the child record (coalesced SoA) at its
  *             global offset
