@@ -525,6 +525,10 @@ int perft_impl(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, int d
             continue;
           }
         }
+        if (lv + 1 >= MAX_LEVELS) {
+          ctx->error = "split_ply exceeds the supported number of breadth-first levels";
+          throw CudaFail{cudaErrorInvalidValue};
+        }
         Level& cur = ctx->levels[lv];
         Level& next = ctx->levels[lv + 1];
         count_and_scan(ctx, cur.rec, cur.cap, 0, cnt, cur.counts, cur.prefix);
