@@ -34,6 +34,21 @@ def test_library_exports_every_declared_symbol():
     assert C.sizeof(_native.PositionStruct) == 112 and C.sizeof(_native.Timing) == 80
 
 
+def test_rust_binding_declares_every_entry_point():
+    """rust/ffi.rs (the `extern "C"` block INTEGRATION.md asks a pabi maintainer to add; not compiled here, there is no
+    rustc) names exactly the functions of include/pabi_cuda.h, with the same number of parameters."""
+    def signatures(text, pattern):
+        out = {}
+        for name, args in re.findall(pattern, text, flags=re.S):
+            args = re.sub(r"/\*.*?\*/", "", args, flags=re.S).strip()
+            out[name] = 0 if args in ("", "void") else args.count(",") + 1
+        return out
+    header = signatures((ROOT / "include" / "pabi_cuda.h").read_text(), r"\b(pabi_(?:cuda|position|move)_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;")
+    rust = signatures((ROOT / "rust" / "ffi.rs").read_text(), r"\bfn\s+(pabi_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*(?:->[^;{]*)?;")
+    assert set(header) == set(rust)
+    assert header == rust
+
+
 def test_no_cpu_fallback_without_a_device():
     import torch
     if torch.cuda.is_available():
