@@ -929,11 +929,13 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
 
   /* K2 takes tiles from a ticket counter (their cost varies, and a static split leaves a tail of idle
    * groups at the end of the launch); K1/K3 tiles are cheap and uniform enough for a static stride */
+  if (LEAF) { /* the ticket of a tile is taken while the tile before it is in phase A, so that its parents can be prefetched */
+    if (tid == 0) sh.next_tile = atomicAdd(out.ticket, 1ULL);
+    group_sync<SYNC>(group);
+  }
   for (size_t tile = (size_t)blockIdx.x * GROUPS + group;; tile += (size_t)gridDim.x * GROUPS) {
     if (LEAF) {
-      if (tid == 0) sh.next_tile = atomicAdd(out.ticket, 1ULL);
-      group_sync<SYNC>(group); /* the scan below separates this read from the next iteration's write */
-      tile = (size_t)sh.next_tile;
+      tile = (size_t)sh.next_tile; /* thread 0 overwrites it only after the next barrier (below) */
     }
     if (tile >= n_tiles) break;
     const size_t i = tile * PARENTS + tid;
@@ -948,6 +950,7 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
       while (lo < tile_parents) {
         if (tid == 0) sh.cursor = 0, sh.overflow = 0;
         group_sync<SYNC>(group);
+        if (tid == 0 && lo == 0 && len == (u32)PARENTS) sh.next_tile = atomicAdd(out.ticket, 1ULL); /* the next tile, once per tile */
         const bool mine = valid && (u32)tid >= lo && (u32)tid < lo + len;
         u32 inert_nodes = 0, inert_moves = 0;
         if (mine) {
@@ -968,6 +971,14 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
           len = len > 1 ? len >> 1 : 1;
           group_sync<SYNC>(group);
           continue;
+        }
+        if (lo == 0 && tid < PARENTS && (tid & 15) == 0) { /* the next tile's parents towards L2, one request per 128-byte line */
+          const size_t next_first = (size_t)sh.next_tile * PARENTS + tid;
+          if (next_first < n) {
+#pragma unroll
+            for (int w = 0; w < POS_WORDS; w++)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(in.rec + (size_t)w * in.stride + first + next_first));
+          }
         }
         inert_children += inert_moves;
         if (MULTI_ROOT) { if (mine) sh.parent_nodes[tid] = inert_nodes; }
