@@ -801,7 +801,7 @@ struct TileGroupShared {
   u32 pool[CFG::POOL];
   u32 parent_nodes[CFG::PARENTS]; /* K2, multi-root: nodes below each parent */
   u64 warp_sums[CFG::GROUP_THREADS / 32 + 1];
-  unsigned long long next_tile; /* TILE_LEAF: the tile this group took from the ticket counter */
+  unsigned long long next_tile; /* TILE_LEAF: the group's next tile (ticket counter), taken while the current tile is in phase A */
   u32 cursor;                   /* TILE_LEAF: pool entries reserved so far, other << 16 | clean (DirectEmitter) */
   u32 overflow;                 /* TILE_LEAF: a reservation did not fit: the range of parents is halved and redone */
 };
