@@ -280,6 +280,88 @@ struct SplitCounter {
   PB_HD void castle(int, int) { ++other; }
 };
 
+/* atomicAdd on the device (shared-memory cursor of a thread group); the host build (tests/native/hostcheck.cpp) is
+ * single-threaded */
+PB_HD u32 fetch_add_u32(u32* p, u32 v) {
+#ifdef __CUDA_ARCH__
+  return atomicAdd(p, v);
+#else
+  const u32 old = *p;
+  *p += v;
+  return old;
+#endif
+}
+
+/* enumerate_split sink of K2 when every parent enumerates its moves ONCE: the slots of a piece's entries are reserved
+ * with one shared-memory atomic on a packed cursor (clean entries grow from the front of the pool, the others from its
+ * end), the inert moves are counted.  A reservation that does not fit raises `overflow`; the kernel then redoes the range
+ * of parents in halves. */
+struct DirectEmitter {
+  u32* pool;
+  u32* cursor;
+  u32* overflow;
+  u32 cap, tag; /* tag = parent << 16 */
+  u64 zone;
+  u32 inert = 0;
+  PB_HD bool reserve(u32 n_clean, u32 n_other, u32& clean_at, u32& other_at) {
+    const u32 old = fetch_add_u32(cursor, n_clean | (n_other << 16));
+    const u32 c0 = old & 0xFFFF, o0 = old >> 16;
+    if (c0 + n_clean + o0 + n_other > cap) {
+      *overflow = 1;
+      return false;
+    }
+    clean_at = c0, other_at = cap - o0 - n_other;
+    return true;
+  }
+  PB_HD void put(u32& at, int from, int to, int promo, int kind) {
+    pool[at++] = ((u32)kind << 28) | tag | pack_move(from, to, promo);
+  }
+  PB_HD void other(u32& at, int from, int to, int kind) {
+    if (kind == KIND_PAWN && to < 8) { /* black promotes on rank 1 */
+      put(at, from, to, PROMO_Q, kind), put(at, from, to, PROMO_R, kind);
+      put(at, from, to, PROMO_B, kind), put(at, from, to, PROMO_N, kind);
+    } else {
+      put(at, from, to, 0, kind);
+    }
+  }
+  PB_HD void piece(int from, int kind, u64 c, u64 o) {
+    const u64 rest = c & ~inert_targets(zone, from, c);
+    inert += popc(c ^ rest);
+    if ((rest | o) == 0) return;
+    u32 clean_at, other_at;
+    if (!reserve(popc(rest), popc(o), clean_at, other_at)) return;
+    for (Squares t(rest); t.any();) put(clean_at, from, t.pop(), 0, kind);
+    for (Squares t(o); t.any();) put(other_at, from, t.pop(), 0, kind);
+  }
+  PB_HD void pushes(u64 c, u64 o, int delta) {
+    const u64 rest = c & ~inert_pushes(zone, c, delta);
+    inert += popc(c ^ rest);
+    if ((rest | o) == 0) return;
+    u32 clean_at, other_at;
+    if (!reserve(popc(rest), popc(o) + 3 * popc(o & RANK_1), clean_at, other_at)) return;
+    for (Squares t(rest); t.any();) {
+      const int to = t.pop();
+      put(clean_at, to + delta, to, 0, KIND_PAWN);
+    }
+    for (Squares t(o); t.any();) {
+      const int to = t.pop();
+      other(other_at, to + delta, to, KIND_PAWN);
+    }
+  }
+  PB_HD void pawn_capture(int from, int to) {
+    u32 clean_at, other_at;
+    if (reserve(0, to < 8 ? 4 : 1, clean_at, other_at)) other(other_at, from, to, KIND_PAWN);
+  }
+  PB_HD void en_passant(int from, int to) {
+    u32 clean_at, other_at;
+    if (reserve(0, 1, clean_at, other_at)) put(other_at, from, to, 0, KIND_PAWN);
+  }
+  PB_HD void castle(int from, int to) {
+    u32 clean_at, other_at;
+    if (reserve(0, 1, clean_at, other_at)) put(other_at, from, to, 0, KIND_KING);
+  }
+};
+
 /* Replies to a clean move: n = the normalised parent (black to move; meta carries base and both king
  * squares), the move is quiet and not a castling move. */
 template <class TB>

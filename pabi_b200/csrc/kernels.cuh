@@ -836,75 +836,7 @@ struct TileOut {
   unsigned long long* ticket;       /* TILE_LEAF: tiles are handed out dynamically (zeroed before the launch) */
 };
 
-/* enumerate_split sink of K2 when every parent enumerates its moves ONCE: the slots of a piece's entries are reserved
- * with one shared-memory atomic on a packed cursor (clean entries grow from the front of the pool, the others from its
- * end), the inert moves are counted.  A reservation that does not fit raises `overflow`; the kernel then redoes the range
- * of parents in halves. */
-struct DirectEmitter {
-  u32* pool;
-  u32* cursor;
-  u32* overflow;
-  u32 cap, tag; /* tag = parent << 16 */
-  u64 zone;
-  u32 inert = 0;
-  __device__ __forceinline__ bool reserve(u32 n_clean, u32 n_other, u32& clean_at, u32& other_at) {
-    const u32 old = atomicAdd(cursor, n_clean | (n_other << 16));
-    const u32 c0 = old & 0xFFFF, o0 = old >> 16;
-    if (c0 + n_clean + o0 + n_other > cap) {
-      *overflow = 1;
-      return false;
-    }
-    clean_at = c0, other_at = cap - o0 - n_other;
-    return true;
-  }
-  __device__ __forceinline__ void put(u32& at, int from, int to, int promo, int kind) {
-    pool[at++] = ((u32)kind << 28) | tag | pack_move(from, to, promo);
-  }
-  __device__ __forceinline__ void other(u32& at, int from, int to, int kind) {
-    if (kind == KIND_PAWN && to < 8) { /* black promotes on rank 1 */
-      put(at, from, to, PROMO_Q, kind), put(at, from, to, PROMO_R, kind);
-      put(at, from, to, PROMO_B, kind), put(at, from, to, PROMO_N, kind);
-    } else {
-      put(at, from, to, 0, kind);
-    }
-  }
-  __device__ __forceinline__ void piece(int from, int kind, u64 c, u64 o) {
-    const u64 rest = c & ~inert_targets(zone, from, c);
-    inert += popc(c ^ rest);
-    if ((rest | o) == 0) return;
-    u32 clean_at, other_at;
-    if (!reserve(popc(rest), popc(o), clean_at, other_at)) return;
-    for (Squares t(rest); t.any();) put(clean_at, from, t.pop(), 0, kind);
-    for (Squares t(o); t.any();) put(other_at, from, t.pop(), 0, kind);
-  }
-  __device__ __forceinline__ void pushes(u64 c, u64 o, int delta) {
-    const u64 rest = c & ~inert_pushes(zone, c, delta);
-    inert += popc(c ^ rest);
-    if ((rest | o) == 0) return;
-    u32 clean_at, other_at;
-    if (!reserve(popc(rest), popc(o) + 3 * popc(o & RANK_1), clean_at, other_at)) return;
-    for (Squares t(rest); t.any();) {
-      const int to = t.pop();
-      put(clean_at, to + delta, to, 0, KIND_PAWN);
-    }
-    for (Squares t(o); t.any();) {
-      const int to = t.pop();
-      other(other_at, to + delta, to, KIND_PAWN);
-    }
-  }
-  __device__ __forceinline__ void pawn_capture(int from, int to) {
-    u32 clean_at, other_at;
-    if (reserve(0, to < 8 ? 4 : 1, clean_at, other_at)) other(other_at, from, to, KIND_PAWN);
-  }
-  __device__ __forceinline__ void en_passant(int from, int to) {
-    u32 clean_at, other_at;
-    if (reserve(0, 1, clean_at, other_at)) put(other_at, from, to, 0, KIND_PAWN);
-  }
-  __device__ __forceinline__ void castle(int from, int to) {
-    u32 clean_at, other_at;
-    if (reserve(0, 1, clean_at, other_at)) put(other_at, from, to, 0, KIND_KING);
-  }
-};
+/* K2's enumerate_split sink, DirectEmitter, lives in incremental.cuh (host-checkable). */
 
 /* In TILE_EXPAND / TILE_MOVES the per-parent counts come from the global scan (`prefix`, built by
  * k_count + k_scan_*), which also fixes where the tile's output starts; in TILE_LEAF they are

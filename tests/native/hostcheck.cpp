@@ -250,6 +250,40 @@ static void incremental_walk(const Pos& p, const Tables& tb, int depth, uint64_t
     PoolSink all{ctx.zone};
     enumerate_split(n, tb, ctx.reach, ctx.guard, all);
     if (all.k != counter.clean + counter.other) ++out[3];
+    /* K2's own sink (DirectEmitter, incremental.cuh): clean entries from the front of the pool, the others from its end,
+     * every entry tagged with the parent, the same set of entries as the PoolSink above, the inert moves counted */
+    constexpr u32 CAP = 1024, TAG = 0x155u << 16;
+    static thread_local u32 pool[CAP + 2];
+    u32 cursor = 0, overflow = 0;
+    {
+      DirectEmitter emit{pool + 1, &cursor, &overflow, CAP, TAG, ctx.zone};
+      pool[0] = pool[CAP + 1] = 0xDEADBEEFu;
+      enumerate_split(n, tb, ctx.reach, ctx.guard, emit);
+      const u32 nc = cursor & 0xFFFF, no = cursor >> 16;
+      if (overflow || nc != counter.clean || no != counter.other || emit.inert != counter.inert || pool[0] != 0xDEADBEEFu ||
+          pool[CAP + 1] != 0xDEADBEEFu) {
+        ++out[3];
+      } else {
+        u32 got[1024], want[1024];
+        for (u32 i = 0; i < nc; i++) got[i] = pool[1 + i];
+        for (u32 i = 0; i < no; i++) got[nc + i] = pool[1 + CAP - no + i] | 0x80000000u;
+        bool ok = true;
+        for (u32 i = 0; i < nc + no; i++) ok &= (got[i] & 0x0FFF0000u) == TAG, got[i] &= ~TAG;
+        for (u32 i = 0; i < all.k; i++) want[i] = all.entries[i];
+        std::sort(got, got + nc + no), std::sort(want, want + all.k);
+        for (u32 i = 0; i < all.k; i++) ok &= got[i] == want[i];
+        if (!ok) ++out[3];
+      }
+    }
+    /* a pool one entry too small: the overflow flag is raised and nothing is written outside it */
+    if (all.k > 1) {
+      const u32 cap = all.k - 1;
+      cursor = 0, overflow = 0;
+      DirectEmitter emit{pool + 1, &cursor, &overflow, cap, TAG, ctx.zone};
+      pool[0] = pool[cap + 1] = 0xDEADBEEFu;
+      enumerate_split(n, tb, ctx.reach, ctx.guard, emit);
+      if (!overflow || pool[0] != 0xDEADBEEFu || pool[cap + 1] != 0xDEADBEEFu) ++out[3];
+    }
   }
   /* the split covers exactly the legal moves */
   uint16_t want[256];
