@@ -268,6 +268,7 @@ def main():
     ap.add_argument("--depth", type=int, default=DEPTH)
     ap.add_argument("--capacity", type=int, default=0, help="frontier records per level buffer (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other_configs legs (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -15,7 +15,13 @@
  *    (cudaError_t).  There is NO CPU fallback: every move-generation, make-move
  *    and perft entry point runs on the device or fails;
  *  - one context owns one device; calls on one context must be serialised by
- *    the caller, different contexts may be used concurrently.
+ *    the caller, different contexts may be used concurrently;
+ *  - positions handed to the device entry points must be positions: built by
+ *    pabi_position_from_fen / _parse / _starting or produced by this library.  A
+ *    record without exactly one king per side or with a pawn on a back rank
+ *    (what the reference's validate() always rejects) makes the call fail with
+ *    status -5; other inconsistencies are the caller's responsibility, as they
+ *    are for the reference's make_move (src/engine/mod.rs:57-64).
  */
 #ifndef PABI_CUDA_H
 #define PABI_CUDA_H
@@ -32,8 +38,11 @@ extern "C" {
 typedef struct {
   uint64_t white[6];          /* king, queens, rooks, bishops, knights, pawns */
   uint64_t black[6];
-  uint64_t hash;              /* carried through, never interpreted (Zobrist keys are build-random,
-                                 src/chess/generated.rs:15-16) */
+  uint64_t hash;              /* Position::hash (src/chess/position.rs:110): set by the parsers (compute_hash,
+                                 :776-806), maintained by every make-move path exactly as make_move does
+                                 (:442-466,491-497,...); never read by move generation or perft.  The
+                                 reference's piece / en passant keys are build-random (generated.rs:15-16,
+                                 build.rs:26-39); here they are fixed and documented (pabi_zobrist_keys) */
   uint16_t fullmove_counter;
   uint8_t castling;           /* src/chess/core.rs:604-612: 1 K, 2 Q, 4 k, 8 q */
   uint8_t side_to_move;       /* src/environment.rs:13-16: 0 white, 1 black */
@@ -75,6 +84,22 @@ int pabi_position_to_fen(const pabi_position_t* p, char* out, size_t cap);
 /* Move::from_uci / impl Display for Move, src/chess/core.rs:105-134 */
 int pabi_move_from_uci(const char* uci, pabi_move_t* out);
 int pabi_move_to_uci(pabi_move_t mv, char out[6]);
+/* Move::flip_perspective, src/chess/core.rs:91-97 (both squares mirrored over the middle of the board, core.rs:231) */
+pabi_move_t pabi_move_flip_perspective(pabi_move_t mv);
+/* Position::hash(), src/chess/position.rs:110: the cached field */
+uint64_t pabi_position_hash(const pabi_position_t* p);
+/* compute_hash, src/chess/position.rs:776-806: the Zobrist hash recomputed from the fields (what the parsers cache) */
+uint64_t pabi_position_compute_hash(const pabi_position_t* p);
+/* Position::num_pieces(), src/chess/position.rs:122-124 */
+uint32_t pabi_position_num_pieces(const pabi_position_t* p);
+/* Position::halfmove_clock_expired(), src/chess/position.rs:750-752 */
+int pabi_position_halfmove_clock_expired(const pabi_position_t* p);
+/* The Zobrist keys (src/chess/generated.rs:7-27): out[0..768) piece keys at player * 384 + kind * 64 + square
+ * (get_piece_key), out[768..776) en passant files, out[776] BLACK_TO_MOVE, out[777..781) WHITE_CAN_CASTLE_SHORT,
+ * WHITE_CAN_CASTLE_LONG, BLACK_CAN_CASTLE_SHORT, BLACK_CAN_CASTLE_LONG.  The last five are the reference's constants;
+ * the first 776 are consecutive splitmix64 outputs from the seed 0x70616269 ("pabi"). */
+#define PABI_ZOBRIST_KEYS 781
+void pabi_zobrist_keys(uint64_t out[PABI_ZOBRIST_KEYS]);
 
 /* ---- device path --------------------------------------------------------- */
 /* device < 0 selects the current CUDA device.  frontier_capacity = positions per
@@ -106,6 +131,11 @@ int pabi_cuda_perft_hashed(pabi_cuda_ctx* ctx, const pabi_position_t* root, uint
  * positions; tests/chess.rs:555-578 loops over a book): nodes_out[i] = perft(roots[i], depth). */
 int pabi_cuda_perft_batch(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, uint8_t depth,
                           uint64_t* nodes_out, pabi_timing_t* timing);
+/* The same with a depth per root: nodes_out[i] = perft(roots[i], depths[i]) -- the reference's perft suite
+ * (tests/chess.rs:622-818, benches/chess.rs:52-86: every vector has its own depth) as ONE call.  Roots of equal
+ * depth are walked together. */
+int pabi_cuda_perft_batch_depths(pabi_cuda_ctx* ctx, const pabi_position_t* roots, const uint8_t* depths, size_t n,
+                                 uint64_t* nodes_out, pabi_timing_t* timing);
 /* Root-subtree sharding for multi-GPU runs: the tree is expanded breadth-first to
  * `split_ply` plies (fewer if the depth is smaller), this call then walks only
  * the subtrees whose index in that frontier is congruent to shard_index modulo
@@ -143,13 +173,14 @@ int pabi_cuda_in_check_batch(pabi_cuda_ctx* ctx, const pabi_position_t* position
 int pabi_cuda_attack_info_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, size_t n,
                                 uint64_t* out /* [5 * n] */, pabi_timing_t* timing);
 /* Position::make_move(&Move), src/chess/position.rs:414-433: out[i] = positions[i] after moves[i]
- * (moves must be legal; the hash field of every device-produced position is 0: the reference's
- * Zobrist keys are build-random, generated.rs:15-16, so hash values cannot be reproduced). */
+ * (moves must be legal).  out[i].hash = positions[i].hash with the XORs make_move applies. */
 int pabi_cuda_make_moves_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, const pabi_move_t* moves,
                                size_t n, pabi_position_t* out, pabi_timing_t* timing);
 /* One breadth-first ply: every child of every position, in generate_moves order
  * (clone + make_move of position.rs:918-920).  children may be NULL to get only
- * the offsets.  Returns -2 when children_cap is too small. */
+ * the offsets.  Returns -2 when children_cap is too small.  All children of one call
+ * must fit one frontier buffer (pabi_cuda_create's frontier_capacity, default 32 Mi
+ * records): a larger batch is an argument error (-1), split it. */
 int pabi_cuda_expand_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions, size_t n,
                            uint32_t* offsets /* [n+1] */, pabi_position_t* children, size_t children_cap,
                            pabi_timing_t* timing);

@@ -135,9 +135,12 @@ static void build_leapers(void) {
   }
 }
 
-/* The reference draws its piece / en-passant Zobrist keys at random on every
- * build (build.rs:26-39), so no key values can be matched; fixed splitmix64
- * keys keep the per-move hashing work of make_move in the CPU baseline. */
+/* Zobrist keys (generated.rs:7-27).  BLACK_TO_MOVE and the four castling keys are the
+ * reference's constants (generated.rs:7-13).  The reference draws its piece and en passant
+ * keys at random on every build (build.rs:26-39), so those values cannot be matched:
+ * they are fixed here as consecutive splitmix64 outputs from the seed 0x70616269 ("pabi"),
+ * 768 piece keys (index player * 384 + kind * 64 + square, generated.rs:22-27) then 8
+ * file keys -- the recipe documented in include/pabi_cuda.h (pabi_zobrist_keys). */
 static uint64_t splitmix64(uint64_t *s) {
   uint64_t z = (*s += 0x9E3779B97F4A7C15ULL);
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
@@ -149,7 +152,11 @@ static void build_keys(void) {
   uint64_t s = 0x70616269ULL; /* "pabi" */
   for (int i = 0; i < 768; i++) ORC_PIECE_KEYS[i] = splitmix64(&s);
   for (int i = 0; i < 8; i++) ORC_EP_KEYS[i] = splitmix64(&s);
-  for (int i = 0; i < 5; i++) ORC_MISC_KEYS[i] = splitmix64(&s);
+  ORC_MISC_KEYS[0] = 0x9E06BAD39D761293ULL; /* BLACK_TO_MOVE, generated.rs:7 */
+  ORC_MISC_KEYS[1] = 0xF05AC573DD61D323ULL; /* WHITE_CAN_CASTLE_SHORT, :9 */
+  ORC_MISC_KEYS[2] = 0x41D8B55BA5FEB78BULL; /* WHITE_CAN_CASTLE_LONG, :10 */
+  ORC_MISC_KEYS[3] = 0x680988787A43D289ULL; /* BLACK_CAN_CASTLE_SHORT, :12 */
+  ORC_MISC_KEYS[4] = 0x2F941F8DFD3E3D1FULL; /* BLACK_CAN_CASTLE_LONG, :13 */
 }
 
 static int g_ready;

@@ -75,7 +75,9 @@ class PabiCudaError(RuntimeError):
 
 EXPORTS = (
     "pabi_position_starting", "pabi_position_from_fen", "pabi_position_parse", "pabi_position_to_fen",
-    "pabi_move_from_uci", "pabi_move_to_uci", "pabi_cuda_create", "pabi_cuda_destroy", "pabi_cuda_last_error",
+    "pabi_move_from_uci", "pabi_move_to_uci", "pabi_move_flip_perspective", "pabi_position_hash", "pabi_position_compute_hash",
+    "pabi_position_num_pieces", "pabi_position_halfmove_clock_expired", "pabi_zobrist_keys", "pabi_cuda_perft_batch_depths",
+    "pabi_cuda_create", "pabi_cuda_destroy", "pabi_cuda_last_error",
     "pabi_cuda_device", "pabi_cuda_host_alloc", "pabi_cuda_host_free", "pabi_cuda_perft", "pabi_cuda_perft_hashed", "pabi_cuda_perft_batch", "pabi_cuda_perft_shard", "pabi_cuda_perft_multi", "pabi_cuda_perft_divide",
     "pabi_cuda_generate_moves_batch", "pabi_cuda_count_moves_batch", "pabi_cuda_in_check_batch",
     "pabi_cuda_attack_info_batch", "pabi_cuda_make_moves_batch", "pabi_cuda_expand_batch", "pabi_cuda_pack_records",
@@ -112,6 +114,18 @@ def lib() -> C.CDLL:
     L.pabi_position_to_fen.argtypes = [P, C.c_char_p, sz]
     L.pabi_move_from_uci.argtypes = [C.c_char_p, C.POINTER(C.c_uint16)]
     L.pabi_move_to_uci.argtypes = [C.c_uint16, C.c_char_p]
+    L.pabi_move_flip_perspective.argtypes = [C.c_uint16]
+    L.pabi_move_flip_perspective.restype = C.c_uint16
+    L.pabi_position_hash.argtypes = [P]
+    L.pabi_position_hash.restype = C.c_uint64
+    L.pabi_position_compute_hash.argtypes = [P]
+    L.pabi_position_compute_hash.restype = C.c_uint64
+    L.pabi_position_num_pieces.argtypes = [P]
+    L.pabi_position_num_pieces.restype = C.c_uint32
+    L.pabi_position_halfmove_clock_expired.argtypes = [P]
+    L.pabi_zobrist_keys.argtypes = [u64p]
+    L.pabi_zobrist_keys.restype = None
+    L.pabi_cuda_perft_batch_depths.argtypes = [vp, vp, vp, sz, vp, T]
     L.pabi_cuda_create.argtypes = [C.c_int, sz, C.POINTER(vp)]
     L.pabi_cuda_destroy.argtypes = [vp]
     L.pabi_cuda_destroy.restype = None

@@ -57,6 +57,10 @@ class Move:
     def promotion(self) -> Optional[str]:
         return (None, "n", "b", "r", "q")[(self.raw >> 12) & 7]
 
+    def flip_perspective(self) -> "Move":
+        """`Move::flip_perspective` (src/chess/core.rs:91-97)."""
+        return Move.from_raw(_native.lib().pabi_move_flip_perspective(self.raw))
+
     def __str__(self) -> str:
         buf = C.create_string_buffer(6)
         _native.lib().pabi_move_to_uci(self.raw, buf)
@@ -150,6 +154,19 @@ class Engine:
         out, t = np.zeros(len(arr), dtype=np.uint64), Timing()
         self._check(_native.lib().pabi_cuda_perft_batch(self._ctx, arr.ctypes.data, len(arr), depth, out.ctypes.data,
                                                         C.byref(t)))
+        self.last_timing = t
+        return out
+
+    def perft_batch_depths(self, positions, depths: Sequence[int]) -> np.ndarray:
+        """`perft(positions[i], depths[i])` for every i in one call (`pabi_cuda_perft_batch_depths`): the shape of the
+        reference's perft suite, where every vector has its own depth."""
+        arr = _as_array(positions)
+        dp = np.ascontiguousarray(np.asarray(depths, dtype=np.uint8))
+        if len(dp) != len(arr):
+            raise ValueError("one depth per position")
+        out, t = np.zeros(len(arr), dtype=np.uint64), Timing()
+        self._check(_native.lib().pabi_cuda_perft_batch_depths(self._ctx, arr.ctypes.data, dp.ctypes.data, len(arr),
+                                                               out.ctypes.data, C.byref(t)))
         self.last_timing = t
         return out
 
@@ -360,10 +377,20 @@ class Position:
         return self.raw.side_to_move ^ 1
 
     def num_pieces(self) -> int:
-        return sum(bin(b).count("1") for b in list(self.raw.white) + list(self.raw.black))
+        """`Position::num_pieces` (position.rs:122-124)."""
+        return _native.lib().pabi_position_num_pieces(C.byref(self.raw))
 
     def halfmove_clock_expired(self) -> bool:
-        return self.raw.halfmove_clock >= 100  # position.rs:750-752
+        """`Position::halfmove_clock_expired` (position.rs:750-752)."""
+        return bool(_native.lib().pabi_position_halfmove_clock_expired(C.byref(self.raw)))
+
+    def hash(self) -> int:
+        """`Position::hash` (position.rs:110): the cached Zobrist hash, set by the parsers and maintained by make_move."""
+        return _native.lib().pabi_position_hash(C.byref(self.raw))
+
+    def compute_hash(self) -> int:
+        """`compute_hash` (position.rs:776-806) over the current fields."""
+        return _native.lib().pabi_position_compute_hash(C.byref(self.raw))
 
     def generate_moves(self, engine: Optional[Engine] = None) -> List[Move]:
         _, moves = (engine or default_engine()).generate_moves_batch([self])
@@ -371,9 +398,7 @@ class Position:
 
     def make_move(self, move: Move, engine: Optional[Engine] = None) -> None:
         out = (engine or default_engine()).make_moves_batch([self], [move.raw])
-        hash_ = self.raw.hash
-        C.memmove(C.byref(self.raw), out.ctypes.data, 112)
-        self.raw.hash = hash_
+        C.memmove(C.byref(self.raw), out.ctypes.data, 112)  # the hash field comes back updated, as make_move does
 
     def attack_info(self, engine: Optional[Engine] = None) -> dict:
         """`Position::attack_info()` (position.rs:285-292)."""
@@ -382,6 +407,13 @@ class Position:
 
     def in_check(self, engine: Optional[Engine] = None) -> bool:
         return bool((engine or default_engine()).in_check_batch([self])[0])
+
+
+def zobrist_keys() -> np.ndarray:
+    """The 781 Zobrist keys in the layout of `pabi_zobrist_keys` (include/pabi_cuda.h)."""
+    out = np.zeros(781, dtype=np.uint64)
+    _native.lib().pabi_zobrist_keys(out.ctypes.data_as(C.POINTER(C.c_uint64)))
+    return out
 
 
 def perft(position: Position, depth: int, engine: Optional[Engine] = None) -> int:

@@ -186,7 +186,22 @@ struct SharedTables {
 struct GlobalTables {
   const u64* rook_attacks; /* [ROOK_TABLE_SIZE] */
   const u64* rays;         /* [64*64], attacks.rs:54-56: [from, to) on a common line, else 0 */
+  const u64* zobrist;      /* [ZOBRIST_KEYS], see below; read only by the paths that maintain Position::hash */
 };
+
+/* Zobrist keys (generated.rs:7-27).  Layout of the key array:
+ *   [0, 768)   piece keys, index player * 384 + kind * 64 + square (get_piece_key, generated.rs:22-27;
+ *              kind in PieceKind order, core.rs:448-455)
+ *   [768, 776) en passant file keys (EN_PASSANT_FILES)
+ *   776        BLACK_TO_MOVE
+ *   777..780   WHITE_CAN_CASTLE_SHORT, WHITE_CAN_CASTLE_LONG, BLACK_CAN_CASTLE_SHORT, BLACK_CAN_CASTLE_LONG
+ *              (bit order of CastleRights, core.rs:604-612)
+ * The last five are the reference's fixed constants (generated.rs:7-13).  The reference draws the piece and en
+ * passant keys at random on every build (build.rs:26-39), so their values cannot be matched; here they are FIXED:
+ * consecutive outputs of splitmix64 seeded with 0x70616269 ("pabi"), 768 piece keys then 8 file keys
+ * (tables.cpp; the oracle uses the same documented recipe). */
+constexpr int ZOBRIST_EP = 768, ZOBRIST_BLACK_TO_MOVE = 776, ZOBRIST_CASTLE = 777, ZOBRIST_KEYS = 781;
+constexpr u64 ZOBRIST_SEED = 0x70616269ULL;
 
 PB_HD u64 ldg64(const u64* p) {
 #ifdef __CUDA_ARCH__
@@ -888,23 +903,73 @@ PB_HD void make_move_kind(Pos& p, const TB& tb, u16 mv, int kind) {
   p.meta = make_meta(castling, ep, us ^ 1, halfmove, fullmove) | kings_known;
 }
 
-/* 64-bit key with the equality semantics of the reference's `Position::hash()` AS MAINTAINED BY
- * make_move, which is what the repetition table sees (game.rs:56, zobrist.rs:10-36).  make_move
- * toggles the piece and castling keys (position.rs:442-466, :491-497, ...) but never toggles
- * BLACK_TO_MOVE (only compute_hash does, :780) and never removes an en passant key once set
- * (:614 is the only use), so within a game two positions have equal hashes exactly when placement
- * and castling rights are equal -- side to move and en passant square do not take part.  The key
- * below is over exactly those fields.  (The Zobrist values themselves are build-random,
- * generated.rs:15-16; different positions collide with probability ~2^-64 here as there.) */
-PB_HD u64 position_key(const Pos& p) {
-  u64 h = 0x9E3779B97F4A7C15ULL;
-  const u64 words[8] = {p.white, p.pawns, p.knights, p.bishops, p.rooks, p.queens, p.kings, p.meta & 0xFULL};
-  for (int i = 0; i < 8; i++) {
-    h = (h ^ words[i]) * 0xBF58476D1CE4E5B9ULL;
-    h ^= h >> 29;
+/* ---- Position::hash (position.rs:110) ------------------------------------------------------ */
+/* compute_hash, position.rs:776-806 */
+template <class TB>
+PB_HD u64 compute_hash(const Pos& p, const TB& tb) {
+  const u64* z = tb.g.zobrist;
+  u64 key = 0;
+  if (meta_stm(p.meta)) key ^= ldg64(z + ZOBRIST_BLACK_TO_MOVE);
+  const int castling = meta_castling(p.meta);
+  for (int i = 0; i < 4; i++)
+    if (castling & (1 << i)) key ^= ldg64(z + ZOBRIST_CASTLE + i);
+  if (meta_ep(p.meta) < NO_SQUARE) key ^= ldg64(z + ZOBRIST_EP + (meta_ep(p.meta) & 7));
+  const u64 sets[6] = {p.pawns, p.knights, p.bishops, p.rooks, p.queens, p.kings};
+  for (int kind = 0; kind < 6; kind++)
+    for (u64 b = sets[kind]; b; b &= b - 1) {
+      const int sq = lsb(b);
+      key ^= ldg64(z + ((p.white >> sq) & 1 ? 0 : 384) + kind * 64 + sq);
+    }
+  return key;
+}
+
+/* What make_move XORs into the hash for move `mv` played in `p` (the position BEFORE the move):
+ * update_castling_rights :442-466, handle_capture :491-497, make_pawn_move :524-531, :536-543, :551-594, :614,
+ * make_king_move :640-696, make_regular_move :714-727.  Faithful to what the reference does NOT do as well: the
+ * BLACK_TO_MOVE key is never toggled and the key of a previous en passant square is never removed. */
+template <class TB>
+PB_HD u64 hash_delta(const Pos& p, const TB& tb, u16 mv) {
+  const u64* z = tb.g.zobrist;
+  const int from = mv & 63, to = (mv >> 6) & 63, promo = (mv >> 12) & 7;
+  const u64 fb = bit(from), tbit = bit(to);
+  const int us = meta_stm(p.meta);
+  const int ours = us * 384, theirs = 384 - ours;
+  const u64 occ = p.pawns | p.knights | p.bishops | p.rooks | p.queens | p.kings;
+  const u64 our = us == 0 ? p.white : occ & ~p.white;
+  u64 d = 0;
+  const int lost = meta_castling(p.meta) & ~(tb.s->keep_from[from] & tb.s->keep_to[to]);
+  for (int i = 0; i < 4; i++)
+    if (lost & (1 << i)) d ^= ldg64(z + ZOBRIST_CASTLE + i);
+  if ((occ & ~our) & tbit) { /* the captured piece: queens, rooks, bishops, knights, pawns (a king is never matched) */
+    const int kind = p.queens & tbit ? KIND_QUEEN : p.rooks & tbit ? KIND_ROOK : p.bishops & tbit ? KIND_BISHOP
+                   : p.knights & tbit ? KIND_KNIGHT : p.pawns & tbit ? KIND_PAWN : -1;
+    if (kind >= 0) d ^= ldg64(z + theirs + kind * 64 + to);
   }
-  h *= 0x94D049BB133111EBULL;
-  return h ^ (h >> 32);
+  if (p.pawns & our & fb) {
+    if (to == meta_ep(p.meta)) d ^= ldg64(z + theirs + KIND_PAWN * 64 + (to & 7) + (from & 56));
+    d ^= ldg64(z + ours + KIND_PAWN * 64 + from);
+    if (promo) { /* Promotion and PieceKind share their numbering: 1 knight .. 4 queen */
+      d ^= ldg64(z + ours + promo * 64 + to);
+    } else {
+      d ^= ldg64(z + ours + KIND_PAWN * 64 + to);
+      if ((from ^ to) == 16) {
+        const u64 beside = ((tbit & ~FILE_H) << 1) | ((tbit & ~FILE_A) >> 1);
+        if (beside & p.pawns & ~our & ~tbit) d ^= ldg64(z + ZOBRIST_EP + (to & 7));
+      }
+    }
+  } else if (p.kings & our & fb) {
+    const int backrank = 56 * us;
+    if (from == backrank + 4 && (to & 56) == backrank) { /* the rook keys are toggled whether or not a rook stands there */
+      if ((to & 7) == 6) d ^= ldg64(z + ours + KIND_ROOK * 64 + backrank + 7) ^ ldg64(z + ours + KIND_ROOK * 64 + backrank + 5);
+      else if ((to & 7) == 2) d ^= ldg64(z + ours + KIND_ROOK * 64 + backrank) ^ ldg64(z + ours + KIND_ROOK * 64 + backrank + 3);
+    }
+    d ^= ldg64(z + ours + KIND_KING * 64 + from) ^ ldg64(z + ours + KIND_KING * 64 + to);
+  } else {
+    const int kind = p.queens & our & fb ? KIND_QUEEN : p.rooks & our & fb ? KIND_ROOK : p.bishops & our & fb ? KIND_BISHOP
+                   : p.knights & our & fb ? KIND_KNIGHT : -1;
+    if (kind >= 0) d ^= ldg64(z + ours + kind * 64 + from) ^ ldg64(z + ours + kind * 64 + to);
+  }
+  return d;
 }
 
 } /* namespace pabi */

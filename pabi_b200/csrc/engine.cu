@@ -19,6 +19,8 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <map>
+#include <set>
 #include <thread>
 #include <vector>
 
@@ -70,6 +72,10 @@ struct pabi_cuda_ctx {
   void* d_tables = nullptr;
   u64* d_rook = nullptr;
   u64* d_rays = nullptr;
+  u64* d_zobrist = nullptr;
+  u32* d_bad_roots = nullptr;      /* k_pack: records that are not positions (replaced by bare kings, the call fails) */
+  u32* h_bad_roots = nullptr;      /* pinned copy, valid after the call's final synchronisation */
+  std::set<const void*> big_smem;  /* tile-kernel instantiations whose dynamic shared-memory limit has been raised */
   Level levels[MAX_LEVELS];
   Level spare; /* shard gather target */
   Level merge_level; /* compaction target of merge_transpositions */
@@ -207,11 +213,13 @@ void scan_counts(pabi_cuda_ctx* ctx, const u32* counts, size_t n, u64* prefix) {
 
 template <TileMode MODE, Accounting ACC, class CFG>
 void launch_tile_cfg(pabi_cuda_ctx* ctx, Frontier in, size_t first, size_t n, const u64* prefix, TileOut out) {
-  static bool configured[8] = {};
-  if (!configured[ctx->device & 7]) { /* the table image alone exceeds the default 48 KB of dynamic shared memory */
+  /* the table image alone exceeds the default 48 KB of dynamic shared memory; the attribute is per device, and a
+   * context is one device used by one caller at a time, so the record of what has been raised lives in the context */
+  const void* fn = (const void*)k_tile<MODE, ACC, CFG>;
+  if (!ctx->big_smem.count(fn)) {
     static_assert(sizeof(TileShared<CFG>) <= 232448, "a tile geometry must fit the 227 KB of shared memory a block may use");
     CK(cudaFuncSetAttribute(k_tile<MODE, ACC, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared<CFG>)));
-    configured[ctx->device & 7] = true;
+    ctx->big_smem.insert(fn);
   }
   const int grid = grid_for(ctx, n, CFG::PARENTS, CFG::MIN_BLOCKS);
   k_tile<MODE, ACC, CFG><<<grid, CFG::THREADS, sizeof(TileShared<CFG>), ctx->stream>>>(ctx->dt, in, first, n, prefix, out);
@@ -444,6 +452,13 @@ struct CallTimer {
   void end_device() { CK(cudaEventRecord(ctx->ev1, ctx->stream)); }
   void finish(pabi_timing_t* t, uint64_t bytes) {
     CK(cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_bad_roots) { /* set by upload_roots' k_pack in this call */
+      const unsigned bad = *ctx->h_bad_roots;
+      *ctx->h_bad_roots = 0;
+      ctx->error = std::to_string(bad) + " input record(s) are not positions (each side needs exactly one king, no pawns on the "
+                   "back ranks): build positions with pabi_position_from_fen / pabi_position_parse";
+      throw CudaFail{(cudaError_t)-5};
+    }
     if (!t) return;
     std::memset(t, 0, sizeof *t);
     float ms = 0;
@@ -468,11 +483,14 @@ void upload_roots(pabi_cuda_ctx* ctx, const pabi_position_t* pos, size_t n) {
   void* staging = ensure(ctx, S_STAGING, n * sizeof(pabi_position_t));
   CK(cudaMemcpyAsync(staging, pos, n * sizeof(pabi_position_t), cudaMemcpyHostToDevice, ctx->stream));
   Level& l0 = ctx->levels[0];
-  k_pack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>((const PositionImage*)staging, n, l0.rec, l0.cap, 0, l0.roots);
+  CK(cudaMemsetAsync(ctx->d_bad_roots, 0, sizeof(u32), ctx->stream));
+  k_pack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>((const PositionImage*)staging, n, l0.rec, l0.cap, 0, l0.roots, ctx->d_bad_roots);
   LAUNCHED();
+  CK(cudaMemcpyAsync(ctx->h_bad_roots, ctx->d_bad_roots, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream)); /* read in CallTimer::finish */
 }
 
 int fail(pabi_cuda_ctx* ctx, const CudaFail& f) {
+  if ((int)f.code < 0) return (int)f.code; /* an argument error found on the device; the message is set */
   if (ctx->error.empty()) ctx->error = cudaGetErrorString(f.code);
   cudaGetLastError();
   return (int)f.code;
@@ -599,9 +617,15 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     CK(cudaMemcpy(ctx->d_tables, &h.shared, sizeof(SharedTables), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_rook, h.rook_attacks, sizeof h.rook_attacks, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_rays, h.rays, sizeof h.rays, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&ctx->d_zobrist, sizeof h.zobrist));
+    CK(cudaMemcpy(ctx->d_zobrist, h.zobrist, sizeof h.zobrist, cudaMemcpyHostToDevice));
     ctx->dt.image = (const SharedTables*)ctx->d_tables;
     ctx->dt.g.rook_attacks = ctx->d_rook;
     ctx->dt.g.rays = ctx->d_rays;
+    ctx->dt.g.zobrist = ctx->d_zobrist;
+    CK(cudaMalloc(&ctx->d_bad_roots, sizeof(u32)));
+    CK(cudaMallocHost(&ctx->h_bad_roots, sizeof(u32)));
+    *ctx->h_bad_roots = 0;
     CK(cudaMalloc(&ctx->d_result, 4 * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_visited, 2 * sizeof(unsigned long long))); /* [0] statistics, [1] tile tickets */
     CK(cudaMallocHost(&ctx->h_result, 4 * sizeof(u64)));
@@ -615,6 +639,7 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     CK(cudaFuncSetAttribute(k_in_check, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_attack_info, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_make_moves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
+    CK(cudaFuncSetAttribute(k_child_hashes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_random_playouts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_leaf_warp<SINGLE_ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeafWarpBlock)));
     CK(cudaFuncSetAttribute(k_moves_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MovesShared)));
@@ -658,6 +683,9 @@ void pabi_cuda_destroy(pabi_cuda_ctx* ctx) {
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_rook) cudaFree(ctx->d_rook);
   if (ctx->d_rays) cudaFree(ctx->d_rays);
+  if (ctx->d_zobrist) cudaFree(ctx->d_zobrist);
+  if (ctx->d_bad_roots) cudaFree(ctx->d_bad_roots);
+  if (ctx->h_bad_roots) cudaFreeHost(ctx->h_bad_roots);
   for (cudaEvent_t e : ctx->leaf_events) cudaEventDestroy(e);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -699,6 +727,34 @@ int pabi_cuda_perft_batch(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size
   }
   if (n > ctx->capacity) return bad_arg(ctx, "more roots than the frontier capacity");
   return perft_impl(ctx, roots, n, depth, nodes_out, PER_ROOT, 0, 0, 1, timing);
+}
+
+int pabi_cuda_perft_batch_depths(pabi_cuda_ctx* ctx, const pabi_position_t* roots, const uint8_t* depths, size_t n,
+                                 uint64_t* nodes_out, pabi_timing_t* timing) {
+  if (!ctx || (n && (!roots || !depths || !nodes_out))) return bad_arg(ctx, "null argument");
+  if (timing) std::memset(timing, 0, sizeof *timing);
+  if (n > ctx->capacity) return bad_arg(ctx, "more roots than the frontier capacity");
+  /* roots of equal depth walk together: one per-root pass per distinct depth */
+  std::map<uint8_t, std::vector<size_t>> groups;
+  for (size_t i = 0; i < n; i++) groups[depths[i]].push_back(i);
+  std::vector<pabi_position_t> batch;
+  std::vector<uint64_t> counts;
+  for (const auto& [depth, members] : groups) {
+    batch.clear();
+    for (size_t i : members) batch.push_back(roots[i]);
+    counts.assign(members.size(), 0);
+    pabi_timing_t t;
+    const int rc = perft_impl(ctx, batch.data(), batch.size(), depth, counts.data(), PER_ROOT, 0, 0, 1, &t);
+    if (rc) return rc;
+    for (size_t k = 0; k < members.size(); k++) nodes_out[members[k]] = counts[k];
+    if (timing) {
+      timing->device_ms += t.device_ms, timing->host_ms += t.host_ms, timing->algorithmic_bytes += t.algorithmic_bytes;
+      timing->kernel_launches += t.kernel_launches, timing->interior_nodes += t.interior_nodes;
+      timing->leaf_kernel_ms += t.leaf_kernel_ms, timing->leaf_kernel_launches += t.leaf_kernel_launches;
+      timing->leaf_parents += t.leaf_parents, timing->leaf_children += t.leaf_children;
+    }
+  }
+  return 0;
 }
 
 int pabi_cuda_perft_shard(pabi_cuda_ctx* ctx, const pabi_position_t* root, uint8_t depth, uint32_t split_ply,
@@ -828,7 +884,8 @@ int pabi_cuda_random_playouts(pabi_cuda_ctx* ctx, const pabi_position_t* starts,
     CK(cudaMemcpyAsync(d_seeds, seeds, n_games * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
     timer.begin_device();
     k_random_playouts<<<grid_for(ctx, n_games, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(
-        ctx->dt, l0.rec, l0.cap, n_games, d_seeds, max_plies, stride, per_game_cap, d_out, d_counts);
+        ctx->dt, l0.rec, l0.cap, n_games, (const PositionImage*)ctx->scratch[S_STAGING].ptr, d_seeds, max_plies, stride, per_game_cap,
+        d_out, d_counts);
     LAUNCHED();
     timer.end_device();
     CK(cudaMemcpyAsync(counts, d_counts, n_games * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
@@ -892,11 +949,18 @@ int pabi_cuda_games_create(pabi_cuda_ctx* ctx, const pabi_position_t* roots, siz
     CK(cudaMemsetAsync(gs.overflow, 0, sizeof(u32), ctx->stream));
     void* staging = ensure(ctx, S_STAGING, n * sizeof(pabi_position_t));
     CK(cudaMemcpyAsync(staging, roots, n * sizeof(pabi_position_t), cudaMemcpyHostToDevice, ctx->stream));
-    k_pack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>((const PositionImage*)staging, n, gs.rec, n, 0, nullptr);
+    CK(cudaMemsetAsync(ctx->d_bad_roots, 0, sizeof(u32), ctx->stream));
+    k_pack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>((const PositionImage*)staging, n, gs.rec, n, 0, nullptr, ctx->d_bad_roots);
     CK(cudaGetLastError());
-    k_games_init<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(gs);
+    k_games_init<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(gs, (const PositionImage*)staging);
     CK(cudaGetLastError());
+    u32 bad = 0;
+    CK(cudaMemcpyAsync(&bad, ctx->d_bad_roots, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (bad) {
+      ctx->error = "a root is not a position (each side needs exactly one king, no pawns on the back ranks)";
+      throw CudaFail{(cudaError_t)-5};
+    }
   } catch (const CudaFail& f) {
     pabi_cuda_games_destroy(games);
     return fail(ctx, f);
@@ -919,6 +983,7 @@ int pabi_cuda_games_actions(pabi_cuda_games* games, uint32_t* offsets, pabi_move
   if (!games || !offsets || (moves_cap && !moves)) return -1;
   pabi_cuda_ctx* ctx = games->ctx;
   try {
+    CK(cudaSetDevice(ctx->device)); /* before any allocation: the scratch must live on the context's device */
     const size_t n = games->gs.n;
     u32* d_offsets = (u32*)ensure(ctx, S_SMALL_A, (n + 1) * sizeof(u32));
     u16* d_moves = moves_cap ? (u16*)ensure(ctx, S_SMALL_B, moves_cap * sizeof(u16)) : nullptr;
@@ -972,7 +1037,7 @@ int pabi_cuda_games_positions(pabi_cuda_games* games, pabi_position_t* out) {
     CK(cudaSetDevice(ctx->device));
     const size_t n = games->gs.n;
     PositionImage* d_out = (PositionImage*)ensure(ctx, S_AOS_OUT, n * sizeof(PositionImage));
-    k_unpack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(games->gs.rec, n, n, d_out);
+    k_games_unpack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(games->gs, d_out);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, d_out, n * sizeof(PositionImage), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1054,14 +1119,15 @@ int pabi_cuda_make_moves_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positi
     upload_roots(ctx, positions, n);
     Level& l0 = ctx->levels[0];
     u16* d_moves = (u16*)ensure(ctx, S_SMALL_A, n * sizeof(u16));
-    u64* d_rec = (u64*)ensure(ctx, S_SMALL_B, n * POS_WORDS * sizeof(u64));
+    u64* d_rec = (u64*)ensure(ctx, S_SMALL_B, n * (POS_WORDS + 1) * sizeof(u64)); /* records, then their hashes */
+    u64* d_hash = d_rec + n * POS_WORDS;
     PositionImage* d_out = (PositionImage*)ensure(ctx, S_AOS_OUT, n * sizeof(PositionImage));
     CK(cudaMemcpyAsync(d_moves, moves, n * sizeof(u16), cudaMemcpyHostToDevice, ctx->stream));
     timer.begin_device();
-    k_make_moves<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, l0.rec, l0.cap, n, d_moves,
-                                                                                            d_rec, n);
+    k_make_moves<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(
+        ctx->dt, l0.rec, l0.cap, n, d_moves, (const PositionImage*)ctx->scratch[S_STAGING].ptr, d_rec, n, d_hash);
     LAUNCHED();
-    k_unpack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(d_rec, n, n, d_out);
+    k_unpack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(d_rec, n, n, d_hash, d_out);
     LAUNCHED();
     timer.end_device();
     CK(cudaMemcpyAsync(out, d_out, n * sizeof(PositionImage), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1114,9 +1180,14 @@ int pabi_cuda_pack_records(pabi_cuda_ctx* ctx, const pabi_position_t* positions,
     if (n == 0) return 0;
     void* staging = ensure(ctx, S_STAGING, n * sizeof(pabi_position_t));
     CK(cudaMemcpyAsync(staging, positions, n * sizeof(pabi_position_t), cudaMemcpyHostToDevice, ctx->stream));
-    k_pack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>((const PositionImage*)staging, n, device_records, stride, 0, nullptr);
+    CK(cudaMemsetAsync(ctx->d_bad_roots, 0, sizeof(u32), ctx->stream));
+    k_pack<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>((const PositionImage*)staging, n, device_records, stride, 0, nullptr,
+                                                            ctx->d_bad_roots);
     CK(cudaGetLastError());
+    u32 bad = 0;
+    CK(cudaMemcpyAsync(&bad, ctx->d_bad_roots, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (bad) return bad_arg(ctx, "an input record is not a position (each side needs exactly one king, no pawns on the back ranks)");
     return 0;
   } catch (const CudaFail& f) {
     return fail(ctx, f);
@@ -1200,7 +1271,11 @@ int pabi_cuda_expand_batch(pabi_cuda_ctx* ctx, const pabi_position_t* positions,
       alloc_level(ctx, l1, ctx->capacity);
       launch_expand(ctx, PER_ROOT, frontier_of(l0), 0, n, l0.prefix, frontier_of(l1));
       PositionImage* d_out = (PositionImage*)ensure(ctx, S_AOS_OUT, total * sizeof(PositionImage));
-      k_unpack<<<grid_for(ctx, total, 256, 8), 256, 0, ctx->stream>>>(l1.rec, l1.cap, total, d_out);
+      u64* d_hash = (u64*)ensure(ctx, S_PREFIX, total * sizeof(u64)); /* Position::hash of every child */
+      k_child_hashes<<<grid_for(ctx, n, FLAT_THREADS, 4), FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(
+          ctx->dt, l0.rec, l0.cap, n, l0.prefix, (const PositionImage*)ctx->scratch[S_STAGING].ptr, d_hash);
+      LAUNCHED();
+      k_unpack<<<grid_for(ctx, total, 256, 8), 256, 0, ctx->stream>>>(l1.rec, l1.cap, total, d_hash, d_out);
       LAUNCHED();
       timer.end_device();
       CK(cudaMemcpyAsync(children, d_out, total * sizeof(PositionImage), cudaMemcpyDeviceToHost, ctx->stream));

@@ -33,6 +33,16 @@ struct ParsedPosition { /* the fields of pabi_position_t */
   u8 castling, stm, halfmove, ep;
 };
 
+/* the 64-byte device record of a parsed position */
+PB_HD Pos record_of(const ParsedPosition& p) {
+  Pos r;
+  r.white = p.white[0] | p.white[1] | p.white[2] | p.white[3] | p.white[4] | p.white[5];
+  r.kings = p.white[0] | p.black[0], r.queens = p.white[1] | p.black[1], r.rooks = p.white[2] | p.black[2];
+  r.bishops = p.white[3] | p.black[3], r.knights = p.white[4] | p.black[4], r.pawns = p.white[5] | p.black[5];
+  r.meta = make_meta(p.castling, p.ep, p.stm, p.halfmove, p.fullmove);
+  return r;
+}
+
 struct FenCursor { /* Rust's `split(' ')`: empty pieces are kept */
   const char* s;
   size_t len, at;

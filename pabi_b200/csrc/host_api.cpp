@@ -162,10 +162,11 @@ pabi_position_t from_fen(std::string_view input) {
     int rights = 0;
     bool ok = !castling->empty();
     if (*castling != "-") {
+      static const char kRights[] = "KQkq";
       int last = -1;
       for (char c : *castling) {
-        const char* at = c ? std::strchr("KQkq", c) : nullptr;
-        const int idx = at ? (int)(at - "KQkq") : -1;
+        const char* at = c ? std::strchr(kRights, c) : nullptr;
+        const int idx = at ? (int)(at - kRights) : -1;
         if (idx <= last) ok = false;
         else rights |= 1 << idx, last = idx;
         if (!ok) break;
@@ -200,7 +201,7 @@ pabi_position_t from_fen(std::string_view input) {
   if (parts.next()) bail("trailing symbols");
   p.halfmove_clock = (uint8_t)halfmove;
   p.fullmove_counter = (uint16_t)fullmove;
-  p.hash = 0; /* Zobrist keys are build-random in the reference (generated.rs:15-16); not reproduced */
+  p.hash = host_compute_hash(pack_record(p)); /* position.rs:266; fixed keys, see chess.cuh */
   try {
     validate(p);
   } catch (ParseError& e) {
@@ -304,7 +305,25 @@ void pabi_position_unpack64(const uint64_t in[8], pabi_position_t* out) {
   Pos r;
   r.white = in[0], r.pawns = in[1], r.knights = in[2], r.bishops = in[3];
   r.rooks = in[4], r.queens = in[5], r.kings = in[6], r.meta = in[7];
-  *out = unpack_record(r, 0);
+  *out = unpack_record(r, host_compute_hash(r)); /* the record carries no hash: it is recomputed as from_fen does */
+}
+
+uint64_t pabi_position_hash(const pabi_position_t* p) { return p ? p->hash : 0; }
+
+uint64_t pabi_position_compute_hash(const pabi_position_t* p) { return p ? host_compute_hash(pack_record(*p)) : 0; }
+
+uint32_t pabi_position_num_pieces(const pabi_position_t* p) {
+  if (!p) return 0;
+  return (uint32_t)popc(side_occupancy(p->white) | side_occupancy(p->black));
+}
+
+int pabi_position_halfmove_clock_expired(const pabi_position_t* p) { return p && p->halfmove_clock >= 100; }
+
+pabi_move_t pabi_move_flip_perspective(pabi_move_t mv) { return (pabi_move_t)(mv ^ (56 | (56 << 6))); }
+
+void pabi_zobrist_keys(uint64_t out[PABI_ZOBRIST_KEYS]) {
+  static_assert(PABI_ZOBRIST_KEYS == ZOBRIST_KEYS, "key table layout");
+  std::memcpy(out, host_tables().zobrist, sizeof(uint64_t) * ZOBRIST_KEYS);
 }
 
 int pabi_move_from_uci(const char* uci, pabi_move_t* out) {
@@ -319,9 +338,10 @@ int pabi_move_from_uci(const char* uci, pabi_move_t* out) {
   }
   int promo = 0;
   if (n == 5) { /* core.rs:707-717 */
-    const char* at = std::strchr("nbrq", uci[4]);
+    static const char kPromotions[] = "nbrq";
+    const char* at = std::strchr(kPromotions, uci[4]);
     if (!at) return -1;
-    promo = (int)(at - "nbrq") + 1;
+    promo = (int)(at - kPromotions) + 1;
   }
   *out = pack_move(sq[0], sq[1], promo);
   return 0;

@@ -44,13 +44,21 @@ __device__ __forceinline__ void stage_tables(SharedTables* dst, const SharedTabl
                  : "memory");
   }
   u32 done = 0;
-  for (u32 spins = 0; !done; ++spins) { /* phase 0 completes when the bytes have landed */
+#ifdef PABI_DEBUG_TRAPS /* debug builds only: a trap is a sticky context error, and a healthy copy can be slow under a profiler */
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+#endif
+  while (!done) { /* phase 0 completes when the bytes have landed */
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(bar)
         : "memory");
-    if (spins > (1u << 20)) __trap(); /* never spin forever on a copy that cannot complete */
+#ifdef PABI_DEBUG_TRAPS
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 5000000000ULL) __trap(); /* five seconds of wall time for a 48 KB copy */
+#endif
   }
 }
 
@@ -58,6 +66,13 @@ struct DeviceTables {
   const SharedTables* image; /* global copy of the shared-memory image */
   GlobalTables g;
 };
+
+struct PositionImage { /* == pabi_position_t (include/pabi_cuda.h) */
+  u64 white[6], black[6], hash;
+  u16 fullmove;
+  u8 castling, stm, halfmove, ep, pad[2];
+};
+static_assert(sizeof(PositionImage) == 112, "pabi_position_t image");
 
 /* SoA view of a frontier: word w of record i at rec[w * stride + i]. */
 struct Frontier {
@@ -199,18 +214,36 @@ k_attack_info(DeviceTables dt, const u64* __restrict__ rec, size_t stride, size_
   }
 }
 
-/* out[i] = rec[i] after moves[i] (position.rs:414-433) */
+/* out[i] = rec[i] after moves[i] (position.rs:414-433); out_hash[i] = the hash field of in_aos[i] with the XORs of make_move */
 __global__ void __launch_bounds__(FLAT_THREADS)
 k_make_moves(DeviceTables dt, const u64* __restrict__ rec, size_t stride, size_t n, const u16* __restrict__ moves,
-             u64* __restrict__ out, size_t out_stride) {
+             const PositionImage* __restrict__ in_aos, u64* __restrict__ out, size_t out_stride, u64* __restrict__ out_hash) {
   extern __shared__ __align__(16) unsigned char smem[];
   SharedTables* st = reinterpret_cast<SharedTables*>(smem);
   stage_tables(st, dt.image);
   const Tables tb{st, dt.g};
   for (size_t i = (size_t)blockIdx.x * FLAT_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * FLAT_THREADS) {
     Pos p = load_pos(rec, stride, i);
+    out_hash[i] = in_aos[i].hash ^ hash_delta(p, tb, moves[i]);
     make_move(p, tb, moves[i]);
     store_pos(out, out_stride, i, p);
+  }
+}
+
+/* Position::hash of the children of one breadth-first ply (pabi_cuda_expand_batch): child k of parent i, in
+ * generate_moves order, gets the parent's hash field with the XORs of make_move (position.rs:414-732) */
+__global__ void __launch_bounds__(FLAT_THREADS)
+k_child_hashes(DeviceTables dt, const u64* __restrict__ rec, size_t stride, size_t n, const u64* __restrict__ prefix,
+               const PositionImage* __restrict__ in_aos, u64* __restrict__ child_hash) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SharedTables* st = reinterpret_cast<SharedTables*>(smem);
+  stage_tables(st, dt.image);
+  const Tables tb{st, dt.g};
+  for (size_t i = (size_t)blockIdx.x * FLAT_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * FLAT_THREADS) {
+    const Pos p = load_pos(rec, stride, i);
+    const u64 h = in_aos[i].hash;
+    u64 at = prefix[i] - prefix[0];
+    generate_moves(p, tb, [&](int from, int to, int promo, int) { child_hash[at++] = h ^ hash_delta(p, tb, pack_move(from, to, promo)); });
   }
 }
 
@@ -221,14 +254,8 @@ __global__ void k_prefix_to_offsets(const u64* __restrict__ prefix, size_t n, u3
 }
 
 /* ---- AoS (pabi_position_t, 112 B) <-> SoA record conversion -------------- */
-struct PositionImage { /* == pabi_position_t */
-  u64 white[6], black[6], hash;
-  u16 fullmove;
-  u8 castling, stm, halfmove, ep, pad[2];
-};
-static_assert(sizeof(PositionImage) == 112, "pabi_position_t image");
 
-__device__ __forceinline__ PositionImage image_of(const Pos& p) {
+__device__ __forceinline__ PositionImage image_of(const Pos& p, u64 hash) {
   PositionImage q;
   const u64 w = p.white;
   q.white[0] = p.kings & w, q.black[0] = p.kings & ~w;
@@ -237,7 +264,7 @@ __device__ __forceinline__ PositionImage image_of(const Pos& p) {
   q.white[3] = p.bishops & w, q.black[3] = p.bishops & ~w;
   q.white[4] = p.knights & w, q.black[4] = p.knights & ~w;
   q.white[5] = p.pawns & w, q.black[5] = p.pawns & ~w;
-  q.hash = 0;
+  q.hash = hash;
   q.fullmove = (u16)meta_fullmove(p.meta);
   q.castling = (u8)meta_castling(p.meta);
   q.stm = (u8)meta_stm(p.meta);
@@ -248,8 +275,11 @@ __device__ __forceinline__ PositionImage image_of(const Pos& p) {
 }
 
 
+/* A record that cannot be a position (not exactly one king per side, pawns on a back rank: what validate() always
+ * rejects, position.rs:934-960) would index the tables out of range; it is replaced by bare kings and counted in
+ * *bad, and the call that uploaded it fails with an argument error. */
 __global__ void k_pack(const PositionImage* __restrict__ in, size_t n, u64* __restrict__ rec, size_t stride, size_t first,
-                       u32* __restrict__ roots) {
+                       u32* __restrict__ roots, u32* __restrict__ bad) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const PositionImage& q = in[i];
     Pos p;
@@ -261,14 +291,22 @@ __global__ void k_pack(const PositionImage* __restrict__ in, size_t n, u64* __re
     p.knights = q.white[4] | q.black[4];
     p.pawns = q.white[5] | q.black[5];
     p.meta = make_meta(q.castling & 15, q.ep > 63 ? NO_SQUARE : q.ep, q.stm & 1, q.halfmove, q.fullmove);
+    if (popc(q.white[0]) != 1 || popc(q.black[0]) != 1 || (p.pawns & (RANK_1 | RANK_8))) {
+      atomicAdd(bad, 1u);
+      p.white = p.kings = bit(0), p.kings |= bit(63);
+      p.pawns = p.knights = p.bishops = p.rooks = p.queens = 0;
+      p.meta = make_meta(0, NO_SQUARE, 0, 0, 1);
+    }
     store_pos(rec, stride, first + i, p);
     if (roots) roots[first + i] = (u32)i;
   }
 }
 
-__global__ void k_unpack(const u64* __restrict__ rec, size_t stride, size_t n, PositionImage* __restrict__ out) {
+/* hash: Position::hash of every record (maintained by the caller's kernel), or null -> 0 */
+__global__ void k_unpack(const u64* __restrict__ rec, size_t stride, size_t n, const u64* __restrict__ hash,
+                         PositionImage* __restrict__ out) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    out[i] = image_of(load_pos(rec, stride, i));
+    out[i] = image_of(load_pos(rec, stride, i), hash ? hash[i] : 0);
 }
 
 __device__ __forceinline__ u64 splitmix64(u64& s) {
@@ -285,8 +323,9 @@ __device__ __forceinline__ u64 splitmix64(u64& s) {
  * recorded until there is no legal move, the halfmove clock reaches 100
  * (Position::halfmove_clock_expired, position.rs:750-752), max_plies, or the game's slots are used. */
 __global__ void __launch_bounds__(FLAT_THREADS)
-k_random_playouts(DeviceTables dt, const u64* __restrict__ rec, size_t stride_rec, size_t n_games, const u64* __restrict__ seeds,
-                  u32 max_plies, u32 stride, u32 per_game_cap, PositionImage* __restrict__ out, u32* __restrict__ counts) {
+k_random_playouts(DeviceTables dt, const u64* __restrict__ rec, size_t stride_rec, size_t n_games, const PositionImage* __restrict__ starts_aos,
+                  const u64* __restrict__ seeds, u32 max_plies, u32 stride, u32 per_game_cap, PositionImage* __restrict__ out,
+                  u32* __restrict__ counts) {
   extern __shared__ __align__(16) unsigned char smem[];
   SharedTables* st = reinterpret_cast<SharedTables*>(smem);
   stage_tables(st, dt.image);
@@ -294,12 +333,13 @@ k_random_playouts(DeviceTables dt, const u64* __restrict__ rec, size_t stride_re
   for (size_t g = (size_t)blockIdx.x * FLAT_THREADS + threadIdx.x; g < n_games; g += (size_t)gridDim.x * FLAT_THREADS) {
     Pos p = load_pos(rec, stride_rec, g);
     u64 seed = seeds[g];
+    u64 hash = starts_aos[g].hash; /* maintained as make_move does, position.rs:414-732 */
     u32 written = 0;
     PositionImage* slot = out + g * per_game_cap;
     for (u32 ply = 0;; ply++) {
       if (ply % stride == 0) {
         if (written >= per_game_cap) break;
-        slot[written++] = image_of(p);
+        slot[written++] = image_of(p, hash);
       }
       if (ply >= max_plies || meta_halfmove(p.meta) >= 100) break;
       const u32 n = count_moves(p, tb);
@@ -310,6 +350,7 @@ k_random_playouts(DeviceTables dt, const u64* __restrict__ rec, size_t stride_re
       generate_moves(p, tb, [&](int from, int to, int promo, int) {
         if (k++ == pick) chosen = pack_move(from, to, promo);
       });
+      hash ^= hash_delta(p, tb, chosen);
       make_move(p, tb, chosen);
     }
     counts[g] = written;
@@ -334,6 +375,7 @@ k_parse_fens(DeviceTables dt, const char* __restrict__ text, const u64* __restri
     PositionImage q;
     for (int k = 0; k < 6; k++) q.white[k] = rc == 0 ? p.white[k] : 0, q.black[k] = rc == 0 ? p.black[k] : 0;
     q.hash = 0;
+    if (rc == 0) q.hash = compute_hash(record_of(p), tb); /* from_fen caches compute_hash(), position.rs:266 */
     q.fullmove = rc == 0 ? p.fullmove : 0, q.castling = rc == 0 ? p.castling : 0, q.stm = rc == 0 ? p.stm : 0;
     q.halfmove = rc == 0 ? p.halfmove : 0, q.ep = rc == 0 ? p.ep : 0, q.pad[0] = q.pad[1] = 0;
     out[i] = q;
@@ -343,7 +385,7 @@ k_parse_fens(DeviceTables dt, const char* __restrict__ text, const u64* __restri
 /* ---- Game environment (game.rs:21-111 without the Syzygy branch), one thread per game ------- */
 struct GamesState {
   u64* rec;          /* SoA records, stride n */
-  u64* keys;         /* keys[g * (history_cap + 1) + k]: key after k actions (RepetitionTable, zobrist.rs:10-36) */
+  u64* keys;         /* keys[g * (history_cap + 1) + k]: Position::hash after k actions (RepetitionTable, zobrist.rs:10-36) */
   u32* plies;        /* actions applied so far */
   u8* perspective;   /* side to move at the root (game.rs:36) */
   u8* threefold;     /* RepetitionTable::record() of the last apply (game.rs:56) */
@@ -375,14 +417,20 @@ __device__ __forceinline__ int game_result(const Pos& p, const TB& tb, bool thre
   return 0;
 }
 
-__global__ void k_games_init(GamesState gs) { /* Game::new, game.rs:30-47 */
+__global__ void k_games_init(GamesState gs, const PositionImage* __restrict__ roots_aos) { /* Game::new, game.rs:30-47 */
   for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < gs.n; g += (size_t)gridDim.x * blockDim.x) {
     const Pos p = load_pos(gs.rec, gs.n, g);
-    gs.keys[g * ((size_t)gs.history_cap + 1)] = position_key(p);
+    gs.keys[g * ((size_t)gs.history_cap + 1)] = roots_aos[g].hash; /* repetitions.record(root.hash()), game.rs:32 */
     gs.plies[g] = 0;
     gs.perspective[g] = (u8)meta_stm(p.meta);
     gs.threefold[g] = 0;
   }
+}
+
+/* the current Position of every game; its hash is the key recorded last (game.rs:56) */
+__global__ void k_games_unpack(GamesState gs, PositionImage* __restrict__ out) {
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < gs.n; g += (size_t)gridDim.x * blockDim.x)
+    out[g] = image_of(load_pos(gs.rec, gs.n, g), gs.keys[g * ((size_t)gs.history_cap + 1) + gs.plies[g]]);
 }
 
 /* Game::apply (game.rs:54-59); action 0xFFFF = leave the game untouched */
@@ -400,9 +448,10 @@ __global__ void __launch_bounds__(FLAT_THREADS) k_games_apply(DeviceTables dt, G
       continue;
     }
     Pos p = load_pos(gs.rec, gs.n, g);
+    const u64 hash = gs.keys[g * ((size_t)gs.history_cap + 1) + ply] ^ hash_delta(p, tb, action);
     make_move(p, tb, action);
     store_pos(gs.rec, gs.n, g, p);
-    gs.threefold[g] = record_key(gs, g, ply + 1, position_key(p));
+    gs.threefold[g] = record_key(gs, g, ply + 1, hash);
     gs.plies[g] = ply + 1;
   }
 }
@@ -430,6 +479,7 @@ k_games_play_random(DeviceTables dt, GamesState gs, const u64* __restrict__ seed
     Pos p = load_pos(gs.rec, gs.n, g);
     u64 seed = seeds[g];
     u32 ply = gs.plies[g], done = 0;
+    u64 hash = gs.keys[g * ((size_t)gs.history_cap + 1) + ply];
     bool threefold = gs.threefold[g] != 0;
     const int perspective = gs.perspective[g];
     int r;
@@ -447,8 +497,9 @@ k_games_play_random(DeviceTables dt, GamesState gs, const u64* __restrict__ seed
       generate_moves(p, tb, [&](int from, int to, int promo, int) {
         if (k++ == pick) chosen = pack_move(from, to, promo);
       });
+      hash ^= hash_delta(p, tb, chosen);
       make_move(p, tb, chosen);
-      threefold = record_key(gs, g, ++ply, position_key(p));
+      threefold = record_key(gs, g, ++ply, hash);
       ++done;
     }
     store_pos(gs.rec, gs.n, g, p);

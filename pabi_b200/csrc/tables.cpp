@@ -174,7 +174,28 @@ static HostTables* build() {
       for (int f = from & 7, r = from >> 3; r * 8 + f != to; f += sf, r += sr) ray |= bit(r * 8 + f);
       t->rays[from * 64 + to] = ray;
     }
+  { /* Zobrist keys: fixed (the reference re-draws the piece and file keys on every build, build.rs:26-39) */
+    u64 state = ZOBRIST_SEED;
+    auto splitmix64 = [&state] {
+      u64 z = (state += 0x9E3779B97F4A7C15ULL);
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+      return z ^ (z >> 31);
+    };
+    for (int i = 0; i < ZOBRIST_BLACK_TO_MOVE; i++) t->zobrist[i] = splitmix64(); /* 768 piece keys, then 8 en passant files */
+    t->zobrist[ZOBRIST_BLACK_TO_MOVE] = 0x9E06BAD39D761293ULL; /* generated.rs:7 */
+    t->zobrist[ZOBRIST_CASTLE + 0] = 0xF05AC573DD61D323ULL;    /* WHITE_CAN_CASTLE_SHORT, generated.rs:9 */
+    t->zobrist[ZOBRIST_CASTLE + 1] = 0x41D8B55BA5FEB78BULL;    /* WHITE_CAN_CASTLE_LONG, generated.rs:10 */
+    t->zobrist[ZOBRIST_CASTLE + 2] = 0x680988787A43D289ULL;    /* BLACK_CAN_CASTLE_SHORT, generated.rs:12 */
+    t->zobrist[ZOBRIST_CASTLE + 3] = 0x2F941F8DFD3E3D1FULL;    /* BLACK_CAN_CASTLE_LONG, generated.rs:13 */
+  }
   return t;
+}
+
+u64 host_compute_hash(const Pos& p) {
+  const HostTables& h = host_tables();
+  const Tables tb{&h.shared, GlobalTables{h.rook_attacks, h.rays, h.zobrist}};
+  return compute_hash(p, tb);
 }
 
 const HostTables& host_tables() {

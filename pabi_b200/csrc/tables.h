@@ -13,6 +13,7 @@ struct HostTables {
   SharedTables shared;              /* image copied to every block's shared memory */
   u64 rook_attacks[ROOK_TABLE_SIZE]; /* global memory, read through L1 */
   u64 rays[64 * 64];                /* RAYS, generated/rays.rs */
+  u64 zobrist[ZOBRIST_KEYS];        /* Zobrist keys in the layout of chess.cuh (generated.rs:7-27) */
 };
 
 /* Built once per process (thread-safe); aborts if a multiply-shift constant
@@ -23,5 +24,8 @@ const HostTables& host_tables();
  * from); exposed for the host-side position code (validation needs checkers). */
 u64 walk_bishop_attacks(int sq, u64 occ);
 u64 walk_rook_attacks(int sq, u64 occ);
+
+/* compute_hash (position.rs:776-806) of a device record, on the host */
+u64 host_compute_hash(const Pos& p);
 
 } /* namespace pabi */

@@ -55,6 +55,12 @@ extern "C" {
     pub fn pabi_position_to_fen(p: *const RawPosition, out: *mut c_char, cap: usize) -> i32;
     pub fn pabi_move_from_uci(uci: *const c_char, out: *mut u16) -> i32;
     pub fn pabi_move_to_uci(mv: u16, out: *mut c_char) -> i32;
+    pub fn pabi_move_flip_perspective(mv: u16) -> u16; // Move::flip_perspective, core.rs:91-97
+    pub fn pabi_position_hash(p: *const RawPosition) -> u64; // Position::hash, position.rs:110
+    pub fn pabi_position_compute_hash(p: *const RawPosition) -> u64; // compute_hash, position.rs:776-806
+    pub fn pabi_position_num_pieces(p: *const RawPosition) -> u32; // position.rs:122-124
+    pub fn pabi_position_halfmove_clock_expired(p: *const RawPosition) -> i32; // position.rs:750-752
+    pub fn pabi_zobrist_keys(out: *mut u64); // 781 keys, layout in include/pabi_cuda.h
 
     pub fn pabi_cuda_create(device: i32, frontier_capacity: usize, out: *mut *mut Ctx) -> i32;
     pub fn pabi_cuda_destroy(ctx: *mut Ctx);
@@ -67,6 +73,8 @@ extern "C" {
     pub fn pabi_cuda_perft_hashed(ctx: *mut Ctx, root: *const RawPosition, depth: u8, nodes: *mut u64, t: *mut Timing) -> i32;
     pub fn pabi_cuda_perft_batch(ctx: *mut Ctx, roots: *const RawPosition, n: usize, depth: u8, nodes_out: *mut u64,
                                  t: *mut Timing) -> i32;
+    pub fn pabi_cuda_perft_batch_depths(ctx: *mut Ctx, roots: *const RawPosition, depths: *const u8, n: usize, nodes_out: *mut u64,
+                                        t: *mut Timing) -> i32;
     pub fn pabi_cuda_perft_shard(ctx: *mut Ctx, root: *const RawPosition, depth: u8, split_ply: u32, shard_index: u32,
                                  shard_count: u32, nodes: *mut u64, t: *mut Timing) -> i32;
     pub fn pabi_cuda_perft_multi(ctxs: *const *mut Ctx, n_ctx: usize, root: *const RawPosition, depth: u8, split_ply: u32,

@@ -25,6 +25,8 @@ def lib() -> C.CDLL:
         L.hostcheck_generate_moves.argtypes = [P, C.POINTER(C.c_uint16)]
         L.hostcheck_make_move.argtypes = [P, C.c_uint16]
         L.hostcheck_in_check.argtypes = [P]
+        L.hostcheck_compute_hash.restype = C.c_uint64
+        L.hostcheck_compute_hash.argtypes = [P]
         L.hostcheck_analysis.argtypes = [P, C.POINTER(C.c_uint64)]
         L.hostcheck_attack_info.argtypes = [P, C.POINTER(C.c_uint64)]
         L.hostcheck_parse.argtypes = [C.c_char_p, C.c_size_t, P]

@@ -20,6 +20,7 @@ static Tables host_tb() {
   t.s = &h.shared;
   t.g.rook_attacks = h.rook_attacks;
   t.g.rays = h.rays;
+  t.g.zobrist = h.zobrist;
   return t;
 }
 
@@ -34,9 +35,12 @@ uint32_t hostcheck_generate_moves(const pabi_position_t* p, uint16_t* out) {
 
 void hostcheck_make_move(pabi_position_t* p, uint16_t mv) {
   Pos r = pack_record(*p);
+  const uint64_t hash = p->hash ^ hash_delta(r, host_tb(), mv); /* Position::hash as make_move maintains it */
   make_move(r, host_tb(), mv);
-  *p = unpack_record(r, p->hash);
+  *p = unpack_record(r, hash);
 }
+
+uint64_t hostcheck_compute_hash(const pabi_position_t* p) { return compute_hash(pack_record(*p), host_tb()); }
 
 int hostcheck_in_check(const pabi_position_t* p) {
   Analysis a;
@@ -64,6 +68,7 @@ int hostcheck_parse(const char* text, size_t len, pabi_position_t* out) {
     for (int k = 0; k < 6; k++) out->white[k] = p.white[k], out->black[k] = p.black[k];
     out->fullmove_counter = p.fullmove, out->castling = p.castling, out->side_to_move = p.stm;
     out->halfmove_clock = p.halfmove, out->en_passant_square = p.ep;
+    out->hash = compute_hash(record_of(p), host_tb()); /* as k_parse_fens does */
   }
   return rc;
 }
@@ -129,7 +134,7 @@ static uint64_t walk_compare(const pabi_position_t& p, int depth, oracle_gen_fn 
     mk(&a, want[i]);
     Pos c = r;
     make_move(c, tb, want[i]);
-    b = unpack_record(c, a.hash);
+    b = unpack_record(c, p.hash ^ hash_delta(r, tb, want[i])); /* all 112 bytes are compared: the hash is the product's own */
     Pos ck = r; /* the counting path's make_move: same board, rights, ep square, side to move */
     make_move_kind(ck, tb, want[i], kinds[i]);
     Pos cc = r; /* K1's make_move: the same with the clocks, i.e. the whole record */

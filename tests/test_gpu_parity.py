@@ -255,8 +255,7 @@ def test_children_equal_oracle_children(engine, playout_positions):
         parent = oracle.Position.from_buffer_copy(batch[i].tobytes())
         for m in want_moves[want_offsets[i]:want_offsets[i + 1]]:
             c = oracle.copy(parent)
-            oracle.make_move(c, int(m))
-            c.hash = 0
+            oracle.make_move(c, int(m))  # hash included: the device maintains Position::hash exactly as make_move does
             assert bytes(c) == children[k].tobytes(), (oracle.to_fen(parent), oracle.move_to_uci(int(m)))
             k += 1
     assert k == len(children)
@@ -277,7 +276,6 @@ def test_random_playouts_on_device_equal_the_oracle_driver(pb, engine):
         total = 0
         for g, got in enumerate(games):
             want = oracle.random_playout(starts[g], seeds[g], max_plies, stride)
-            want["hash"] = 0
             assert got.tobytes() == want.tobytes(), (g, max_plies, stride)
             total += len(got)
         assert total >= 600
@@ -367,8 +365,7 @@ def test_random_self_play_equals_the_oracle_game(pb, engine):
         r, n = og.play_random(seeds[g], 600)
         assert (results[g], int(plies[g])) == (r, n), g
         want = og.position()
-        want.hash = 0
-        assert bytes(want) == finals[g].tobytes(), g
+        assert bytes(want) == finals[g].tobytes(), g  # all 112 bytes, Position::hash included
         tally[r] = tally.get(r, 0) + 1
     assert tally.get("draw", 0) > 0 and (tally.get("win", 0) + tally.get("loss", 0)) > 0
     assert games.result() == results                                          # Game::result agrees after the fact
@@ -477,3 +474,107 @@ def test_one_million_move_lists_bit_exact(engine):
 def test_startpos_perft_8(pb, engine):
     """configs[3]: 84 998 978 956 nodes."""
     assert engine.perft(pb.Position.starting(), 8) == 84_998_978_956
+
+
+# ---- round 2: Position::hash on the device, per-root depths, the C consumer, refused records ----
+
+def test_reference_hash_properties_with_make_move_on_the_device(pb, engine):
+    """tests/chess.rs:820-868 (repetition_hash, castling_hash): the hash is maintained by the device make_move."""
+    p = pb.Position.try_from("8/5k2/6p1/8/8/8/1p3P2/5K2 w - - 0 1")
+    initial = p.hash()
+    assert initial == p.compute_hash() != 0
+    for uci in ("f1e2", "f7f6", "e2f1"):
+        p.make_move(pb.Move.from_uci(uci), engine)
+        assert p.hash() != initial
+    p.make_move(pb.Move.from_uci("f6f7"), engine)
+    assert str(p) == "8/5k2/6p1/8/8/8/1p3P2/5K2 w - - 4 3" and p.hash() == initial
+    p = pb.Position.try_from("rnbqk1nr/p3bppp/1p2p3/2ppP3/3P4/P7/1PP1NPPP/R1BQKBNR w KQkq - 0 7")
+    initial = p.hash()
+    for uci in ("e1d2", "e8d7", "d2e1", "d7e8"):
+        p.make_move(pb.Move.from_uci(uci), engine)
+    assert str(p) == "rnbqk1nr/p3bppp/1p2p3/2ppP3/3P4/P7/1PP1NPPP/R1BQKBNR w - - 4 9" and p.hash() != initial
+
+
+def test_hash_of_every_child_equals_the_oracles(pb, engine, vectors):
+    """Device `hash` == oracle `hash` on every child of the reference trees (two plies below every perft vector's
+    root, all 112 bytes compared), and on every line parsed on the device."""
+    roots = [oracle.parse(c["fen"]) for c in vectors["perft"] + vectors["bench_perft"]]
+    level = oracle.positions_array(roots)
+    for _ in range(2):
+        offsets, children = engine.expand_batch(level)
+        want_offsets, want_moves = oracle.generate_moves_batch(level)
+        assert np.array_equal(offsets, want_offsets)
+        want = np.zeros(len(children), dtype=level.dtype)
+        k = 0
+        for i in range(len(level)):
+            parent = oracle.Position.from_buffer_copy(level[i].tobytes())
+            for m in want_moves[want_offsets[i]:want_offsets[i + 1]]:
+                c = oracle.copy(parent)
+                oracle.make_move(c, int(m))
+                C.memmove(want.ctypes.data + 112 * k, C.byref(c), 112)
+                k += 1
+        assert k == len(children) and children.tobytes() == want.tobytes()
+        assert len(np.unique(children["hash"])) > 0.5 * len(children)
+        level = np.ascontiguousarray(children[:: max(1, len(children) // 3000)])
+    lines = [oracle.to_fen(oracle.Position.from_buffer_copy(level[i].tobytes())) for i in range(0, len(level), 3)]
+    positions, status = engine.parse_batch(lines)
+    assert not status.any()
+    for line, got in zip(lines, positions):
+        assert got.tobytes() == bytes(oracle.from_fen(line))
+
+
+def test_perft_suite_as_one_batch_with_per_root_depths(pb, engine, small_engine, vectors):
+    """the whole reference suite through one call (`pabi_cuda_perft_batch_depths`)."""
+    cases = [c for c in vectors["perft"] + vectors["bench_perft"] if c["nodes"] < 2_000_000_000]
+    roots = oracle.positions_array([oracle.parse(c["fen"]) for c in cases])
+    depths = [c["depth"] for c in cases]
+    assert engine.perft_batch_depths(roots, depths).tolist() == [c["nodes"] for c in cases]
+    light = [i for i, c in enumerate(cases) if c["nodes"] < 50_000_000]
+    got = small_engine.perft_batch_depths(np.ascontiguousarray(roots[light]), [depths[i] for i in light])
+    assert got.tolist() == [cases[i]["nodes"] for i in light]
+    assert engine.perft_batch_depths(roots[:0], []).tolist() == []
+
+
+def test_records_that_are_not_positions_are_refused(pb, engine):
+    bad = np.zeros(3, dtype=pb.POSITION_DTYPE)
+    bad[0] = np.frombuffer(bytes(pb.Position.starting().raw), dtype=pb.POSITION_DTYPE)[0]
+    bad[2] = bad[0]
+    bad[2]["white"][5] |= 1 << 60                       # a white pawn on the eighth rank
+    for call in (lambda: engine.perft_batch(bad, 3), lambda: engine.generate_moves_batch(bad), lambda: engine.count_moves_batch(bad),
+                 lambda: pb.Games(engine, bad)):
+        with pytest.raises(pb.PabiCudaError) as e:
+            call()
+        assert e.value.status == -5 and "not" in str(e.value)
+    assert engine.perft(pb.Position.starting(), 4) == 197281  # the context is unharmed
+
+
+def test_c_consumer_of_the_header_runs_a_perft(tmp_path):
+    """tests/native/abi_smoke.c linked against the library: struct layouts asserted with offsetof, one perft and one
+    per-root-depth batch through include/pabi_cuda.h from plain C."""
+    import subprocess
+    from pathlib import Path
+    from pabi_b200 import _native
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "abi_smoke"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", str(root / "include"), str(root / "tests/native/abi_smoke.c"),
+                    "-o", str(exe), "-L", str(_native.PKG_DIR), "-lpabi_b200", f"-Wl,-rpath,{_native.PKG_DIR}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "device perft ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_games_on_one_device_while_another_context_is_current(pb, engine):
+    """every entry point selects its context's device before it allocates.  With two devices, calls on
+    Engine(1) are interleaved with a Games object that lives on Engine(0)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two devices")
+    other = pb.Engine(1)
+    games = pb.Games(engine, oracle.positions_array([oracle.starting()] * 64), history_cap=64)
+    assert other.perft(pb.Position.starting(), 4) == 197281           # leaves device 1 current on this thread
+    offsets, moves = games.actions()
+    assert offsets[-1] == 64 * 20
+    assert other.perft(pb.Position.starting(), 3) == 8902
+    games.apply([int(moves[offsets[g]]) for g in range(64)])
+    assert games.result() == [None] * 64
+    games.close()
+    other.close()

@@ -26,7 +26,7 @@ def sanitize_fen(text: str) -> str:
 
 def test_library_exports_every_declared_symbol():
     header = (ROOT / "include" / "pabi_cuda.h").read_text()
-    declared = set(re.findall(r"\b(pabi_(?:cuda|position|move)_[a-z0-9_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(pabi_(?:cuda|position|move|zobrist)_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_native.EXPORTS)
     L = _native.lib()
     for name in declared:
@@ -43,8 +43,8 @@ def test_rust_binding_declares_every_entry_point():
             args = re.sub(r"/\*.*?\*/", "", args, flags=re.S).strip()
             out[name] = 0 if args in ("", "void") else args.count(",") + 1
         return out
-    header = signatures((ROOT / "include" / "pabi_cuda.h").read_text(), r"\b(pabi_(?:cuda|position|move)_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;")
-    rust = signatures((ROOT / "rust" / "ffi.rs").read_text(), r"\bfn\s+(pabi_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*(?:->[^;{]*)?;")
+    header = signatures((ROOT / "include" / "pabi_cuda.h").read_text(), r"\b(pabi_(?:cuda|position|move|zobrist)_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;")
+    rust = signatures((ROOT / "rust" / "ffi.rs").read_text(), r"\bfn\s+(pabi_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*(?:->[^;{/]*)?;")
     assert set(header) == set(rust)
     assert header == rust
 
@@ -74,9 +74,7 @@ def test_basic_positions_round_trip(vectors):
     for fen in vectors["fen"]["roundtrip"]:
         p = pb.Position.from_fen(fen)
         assert str(p) == sanitize_fen(fen)
-        o = oracle.from_fen(fen)
-        o.hash = 0
-        assert bytes(p.raw) == bytes(o)
+        assert bytes(p.raw) == bytes(oracle.from_fen(fen))  # all 112 bytes: Position::hash is compute_hash on both sides
 
 
 def test_validation_error_strings(vectors):
@@ -140,8 +138,7 @@ def test_accepts_what_the_oracle_accepts_on_playout_positions():
             fen = oracle.to_fen(o)
             p = pb.Position.from_fen(fen)
             assert str(p) == fen
-            o.hash = 0
-            assert bytes(p.raw) == bytes(o)
+            assert bytes(p.raw) == bytes(oracle.from_fen(fen))  # the parser caches compute_hash (position.rs:266)
 
 
 def test_fen_supplied_ep_square_kept_verbatim():
@@ -173,3 +170,70 @@ def test_pack64_round_trip():
             assert len(words) == 8
             q = pb.Position.unpack64(words)
             assert bytes(q.raw) == bytes(p.raw)
+
+
+# ---- Position::hash and the small accessors of the boundary ----
+
+def _splitmix64(state):
+    state = (state + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = state
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return state, z ^ (z >> 31)
+
+
+def test_zobrist_keys_follow_the_documented_recipe():
+    """include/pabi_cuda.h: 776 splitmix64 outputs from the seed "pabi", then the reference's five constants
+    (src/chess/generated.rs:7-13)."""
+    keys = pb.chess.zobrist_keys()
+    state = 0x70616269
+    for i in range(776):
+        state, want = _splitmix64(state)
+        assert int(keys[i]) == want, i
+    assert [int(k) for k in keys[776:]] == [0x9E06BAD39D761293, 0xF05AC573DD61D323, 0x41D8B55BA5FEB78B,
+                                            0x680988787A43D289, 0x2F941F8DFD3E3D1F]
+    assert len(set(int(k) for k in keys)) == 781
+
+
+def test_hash_of_parsed_positions_is_compute_hash_and_equals_the_oracles(vectors):
+    import hostcheck
+    fens = list(vectors["fen"]["roundtrip"]) + [c["fen"] for c in vectors["perft"] if c["fen"] != "startpos"]
+    for fen in fens:
+        p, o = pb.Position.try_from(fen), oracle.parse(fen)
+        assert p.hash() == p.compute_hash() == o.hash == oracle.lib().oracle_compute_hash(C.byref(o))
+        assert hostcheck.lib().hostcheck_compute_hash(C.byref(o)) == o.hash  # the device function, compiled for the host
+
+
+def test_hash_properties_of_the_reference():
+    """tests/chess.rs:840-868: the parts that need no make_move (en_passant_hash, castling_hash's first assertion,
+    move_clock_hash); the make_move parts run on the device (tests/test_gpu_parity.py)."""
+    h = lambda fen: pb.Position.try_from(fen).hash()
+    assert h("6qk/8/8/3Pp3/8/8/K7/8 w - e6 0 1") != h("6qk/8/8/3Pp3/8/8/K7/8 w - - 0 1")
+    assert h("rnbqk1nr/p3bppp/1p2p3/2ppP3/3P4/P7/1PP1NPPP/R1BQKBNR w KQkq - 0 7") != \
+        h("rnbqk1nr/p3bppp/1p2p3/2ppP3/3P4/P7/1PP1NPPP/R1BQKBNR w Qkq - 0 7")
+    assert h("6qk/8/8/3Pp3/8/8/K7/8 w - - 0 1") == h("6qk/8/8/3Pp3/8/8/K7/8 w - - 2 3")
+    assert h("6qk/8/8/3Pp3/8/8/K7/8 w - - 0 1") != h("6qk/8/8/3Pp3/8/8/K7/8 b - - 0 1")
+
+
+def test_small_accessors():
+    start = pb.Position.starting()
+    assert start.num_pieces() == 32 and not start.halfmove_clock_expired()                  # position.rs:122-124
+    late = pb.Position.from_fen("8/5k2/3p4/1p1Pp2p/pP2Pp1P/P4P1K/8/8 b - - 100 80")
+    assert late.num_pieces() == 14 and late.halfmove_clock_expired()                       # position.rs:750-752
+    assert not pb.Position.from_fen("8/5k2/3p4/1p1Pp2p/pP2Pp1P/P4P1K/8/8 b - - 99 80").halfmove_clock_expired()
+    # core.rs:83-90 doc-test: E1 -> E8 flipped is E8 -> E1; the promotion is kept
+    assert pb.Move(4, 60).flip_perspective() == pb.Move(60, 4)
+    assert pb.Move.from_uci("a7a8q").flip_perspective() == pb.Move.from_uci("a2a1q")
+    assert pb.Move.from_uci("d4d5").flip_perspective() == pb.Move.from_uci("d5d4")          # core.rs:227-228
+
+
+def test_c_consumer_of_the_header(tmp_path):
+    """tests/native/abi_smoke.c: a C11 translation unit that includes include/pabi_cuda.h, asserts both struct layouts
+    with offsetof and links the library (host entry points only here; with a device it also runs one perft)."""
+    import subprocess
+    exe = tmp_path / "abi_smoke"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", str(ROOT / "include"), str(ROOT / "tests/native/abi_smoke.c"),
+                    "-o", str(exe), "-L", str(_native.PKG_DIR), "-lpabi_b200", f"-Wl,-rpath,{_native.PKG_DIR}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "layout ok" in out.stdout and "text api ok" in out.stdout
