@@ -514,7 +514,7 @@ def test_hash_of_every_child_equals_the_oracles(pb, engine, vectors):
                 C.memmove(want.ctypes.data + 112 * k, C.byref(c), 112)
                 k += 1
         assert k == len(children) and children.tobytes() == want.tobytes()
-        assert len(np.unique(children["hash"])) > 0.5 * len(children)
+        assert children["hash"].all()  # the suite repeats roots at several depths, so equal hashes are expected; zero is not
         level = np.ascontiguousarray(children[:: max(1, len(children) // 3000)])
     lines = [oracle.to_fen(oracle.Position.from_buffer_copy(level[i].tobytes())) for i in range(0, len(level), 3)]
     positions, status = engine.parse_batch(lines)
@@ -578,3 +578,18 @@ def test_games_on_one_device_while_another_context_is_current(pb, engine):
     assert games.result() == [None] * 64
     games.close()
     other.close()
+
+
+def test_device_side_workload_generators_reproduce_the_oracle_workloads(pb, engine):
+    """pabi_b200/workloads.py builds the stand-in book and the 1 M playout positions with the device playout kernel; both are
+    byte-identical (Position::hash included) to the oracle-built workloads whose digests tests/golden/workload_fixtures.json holds."""
+    import hashlib
+    import json
+    from pathlib import Path
+    from pabi_b200 import workloads as W
+    fx = json.loads((Path(__file__).resolve().parent / "golden" / "workload_fixtures.json").read_text())
+    book = W.chess324_synth_book(engine)
+    assert len(book) == 1620 and hashlib.sha256(book.tobytes()).hexdigest() == fx["book"]["sha256"]
+    assert engine.perft_batch(book, 4).tolist() == fx["book"]["perft"]
+    positions = W.playout_positions(engine, 1_000_000)
+    assert hashlib.sha256(positions.tobytes()).hexdigest() == fx["playouts"]["sha256"]

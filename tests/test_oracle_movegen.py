@@ -121,3 +121,25 @@ def test_batch_and_playout_helpers():
     for i in (0, 1, len(a) - 1):
         p = oracle.Position.from_buffer_copy(a[i].tobytes())
         assert list(moves[offsets[i]:offsets[i + 1]]) == oracle.generate_moves(p)
+
+
+def test_workload_fixtures_are_the_oracles_answers():
+    """tests/golden/workload_fixtures.json (what bench.py checks the GPU's other_configs against) is reproducible from the
+    oracle: same digests for the stand-in book and the first 100 000 playout positions' worth of the 1 M workload."""
+    import hashlib
+    import json
+    from pathlib import Path
+    import numpy as np
+    import workloads
+    fx = json.loads((Path(__file__).resolve().parent / "golden" / "workload_fixtures.json").read_text())
+    book = workloads.chess324_synth_book()
+    assert hashlib.sha256(book.tobytes()).hexdigest() == fx["book"]["sha256"] and len(fx["book"]["perft"]) == len(book) == 1620
+    for i in range(0, len(book), 97):
+        assert oracle.perft(oracle.Position.from_buffer_copy(book[i].tobytes()), 4) == fx["book"]["perft"][i]
+    assert sum(fx["book"]["perft"]) == fx["book"]["nodes"]
+    positions = workloads.playout_positions(1_000_000)
+    assert hashlib.sha256(positions.tobytes()).hexdigest() == fx["playouts"]["sha256"]
+    offsets, moves = oracle.generate_moves_batch(positions)
+    assert len(moves) == fx["playouts"]["moves"]
+    assert hashlib.sha256(offsets.tobytes()).hexdigest() == fx["playouts"]["offsets_sha256"]
+    assert hashlib.sha256(moves.tobytes()).hexdigest() == fx["playouts"]["moves_sha256"]
