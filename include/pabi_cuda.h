@@ -109,6 +109,11 @@ void pabi_cuda_destroy(pabi_cuda_ctx* ctx);
 const char* pabi_cuda_last_error(pabi_cuda_ctx* ctx);
 int pabi_cuda_device(const pabi_cuda_ctx* ctx);
 
+/* Checking builds only (`make -C pabi_b200/csrc bounds`, -DPABI_BOUNDS): the source line of the first out-of-range
+ * record or pool index any kernel has computed since the last call (0 = none; the offending access was skipped), or -1
+ * when the library was built without the checks (the shipped build). */
+int pabi_cuda_bounds_violation(pabi_cuda_ctx* ctx);
+
 /* Page-locked host memory for the arrays of the batched calls below (new; the reference has no counterpart).  Buffers
  * from here are copied to and from the device at the speed of the link instead of through the driver's staging
  * copy of pageable memory (1 M positions in, 27.6 M moves out: 24.7 ms -> 3.4 ms end to end on a B200 box).  Any host pointer is

@@ -76,7 +76,7 @@ class PabiCudaError(RuntimeError):
 EXPORTS = (
     "pabi_position_starting", "pabi_position_from_fen", "pabi_position_parse", "pabi_position_to_fen",
     "pabi_move_from_uci", "pabi_move_to_uci", "pabi_move_flip_perspective", "pabi_position_hash", "pabi_position_compute_hash",
-    "pabi_position_num_pieces", "pabi_position_halfmove_clock_expired", "pabi_zobrist_keys", "pabi_cuda_perft_batch_depths",
+    "pabi_position_num_pieces", "pabi_position_halfmove_clock_expired", "pabi_zobrist_keys", "pabi_cuda_perft_batch_depths", "pabi_cuda_bounds_violation",
     "pabi_cuda_create", "pabi_cuda_destroy", "pabi_cuda_last_error",
     "pabi_cuda_device", "pabi_cuda_host_alloc", "pabi_cuda_host_free", "pabi_cuda_perft", "pabi_cuda_perft_hashed", "pabi_cuda_perft_batch", "pabi_cuda_perft_shard", "pabi_cuda_perft_multi", "pabi_cuda_perft_divide",
     "pabi_cuda_generate_moves_batch", "pabi_cuda_count_moves_batch", "pabi_cuda_in_check_batch",
@@ -132,6 +132,7 @@ def lib() -> C.CDLL:
     L.pabi_cuda_last_error.argtypes = [vp]
     L.pabi_cuda_last_error.restype = C.c_char_p
     L.pabi_cuda_device.argtypes = [vp]
+    L.pabi_cuda_bounds_violation.argtypes = [vp]
     L.pabi_cuda_host_alloc.argtypes = [sz, C.POINTER(vp)]
     L.pabi_cuda_host_free.argtypes = [vp]
     L.pabi_cuda_host_free.restype = None

@@ -131,6 +131,11 @@ class Engine:
     def device(self) -> int:
         return _native.lib().pabi_cuda_device(self._ctx)
 
+    def bounds_violation(self) -> int:
+        """Checking builds (-DPABI_BOUNDS): source line of the first out-of-range index since the last call, 0 = none;
+        -1 in the shipped build."""
+        return _native.lib().pabi_cuda_bounds_violation(self._ctx)
+
     def _check(self, rc: int) -> None:
         if rc != 0:
             raise PabiCudaError(rc, _native.lib().pabi_cuda_last_error(self._ctx).decode())

@@ -118,8 +118,27 @@ PB_HD u64 make_meta(int castling, int ep, int stm, int halfmove, int fullmove) {
          ((u64)fullmove << 32);
 }
 
+/* -DPABI_BOUNDS (a checking build, `make bounds`): every record access and every shared-memory pool access of the
+ * kernels tests its index; a violation records its source line (the first one wins) and the access is skipped.
+ * compute-sanitizer is not available on this GPU pool, so the GPU test-suite is run once against this build instead
+ * (tools/bounds_suite.sh); pabi_cuda_bounds_violation() reads the line back. */
+#if defined(PABI_BOUNDS) && defined(__CUDACC__)
+__device__ unsigned int g_bounds_violation = 0;
+#endif
+#if defined(PABI_BOUNDS) && defined(__CUDA_ARCH__)
+__device__ __forceinline__ bool in_bounds(unsigned long long i, unsigned long long n, int line) {
+  if (i < n) return true;
+  atomicCAS(&g_bounds_violation, 0u, (unsigned int)line);
+  return false;
+}
+#define PB_IN_BOUNDS(i, n) pabi::in_bounds((unsigned long long)(i), (unsigned long long)(n), __LINE__)
+#else
+#define PB_IN_BOUNDS(i, n) true
+#endif
+
 PB_HD Pos load_pos(const u64* __restrict__ base, size_t stride, size_t i) {
   Pos p;
+  if (!PB_IN_BOUNDS(i, stride)) i = 0;
   p.white = base[0 * stride + i];
   p.pawns = base[1 * stride + i];
   p.knights = base[2 * stride + i];
@@ -131,6 +150,7 @@ PB_HD Pos load_pos(const u64* __restrict__ base, size_t stride, size_t i) {
   return p;
 }
 PB_HD void store_pos(u64* __restrict__ base, size_t stride, size_t i, const Pos& p) {
+  if (!PB_IN_BOUNDS(i, stride)) return;
   base[0 * stride + i] = p.white;
   base[1 * stride + i] = p.pawns;
   base[2 * stride + i] = p.knights;

@@ -696,6 +696,21 @@ void pabi_cuda_destroy(pabi_cuda_ctx* ctx) {
 const char* pabi_cuda_last_error(pabi_cuda_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
 int pabi_cuda_device(const pabi_cuda_ctx* ctx) { return ctx ? ctx->device : -1; }
 
+int pabi_cuda_bounds_violation(pabi_cuda_ctx* ctx) {
+#ifdef PABI_BOUNDS
+  if (!ctx) return -1;
+  unsigned int line = 0, zero = 0;
+  if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
+      cudaMemcpyFromSymbol(&line, g_bounds_violation, sizeof line) != cudaSuccess ||
+      cudaMemcpyToSymbol(g_bounds_violation, &zero, sizeof zero) != cudaSuccess)
+    return -2;
+  return (int)line;
+#else
+  (void)ctx;
+  return -1;
+#endif
+}
+
 int pabi_cuda_host_alloc(size_t bytes, void** out) {
   if (!out) return -1;
   *out = nullptr;

@@ -314,7 +314,8 @@ struct DirectEmitter {
     return true;
   }
   PB_HD void put(u32& at, int from, int to, int promo, int kind) {
-    pool[at++] = ((u32)kind << 28) | tag | pack_move(from, to, promo);
+    if (PB_IN_BOUNDS(at, cap)) pool[at] = ((u32)kind << 28) | tag | pack_move(from, to, promo);
+    ++at;
   }
   PB_HD void other(u32& at, int from, int to, int kind) {
     if (kind == KIND_PAWN && to < 8) { /* black promotes on rank 1 */

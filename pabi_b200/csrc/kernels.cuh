@@ -649,7 +649,8 @@ k_root_levels(DeviceTables dt, RootLevels lv, u32 n, int max_plies, u64* __restr
       if (cnt) {
         u32 j = off;
         generate_moves(p, tb, [&](int from, int to, int promo, int kind) {
-          rs.pool[j++] = ((u32)kind << 28) | ((u32)tid << 16) | pack_move(from, to, promo);
+          if (PB_IN_BOUNDS(j, ROOT_POOL)) rs.pool[j] = ((u32)kind << 28) | ((u32)tid << 16) | pack_move(from, to, promo);
+          ++j;
         });
       }
       __syncthreads();
@@ -971,8 +972,9 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         if (tid == 0 && end) atomicAdd(out.visited, (unsigned long long)end); /* statistics: positions at the last ply but one */
         if (MULTI_ROOT) group_sync<SYNC>(group); /* the per-parent counters are set */
         for (u32 c = tid; c < end; c += GT) {
-          const u32 e = sh.pool[c < clean_here ? c : POOL - others + (c - clean_here)];
-          const int parent = (e >> 16) & 0xFFF;
+          const u32 slot = c < clean_here ? c : POOL - others + (c - clean_here);
+          const u32 e = PB_IN_BOUNDS(slot, POOL) ? sh.pool[slot] : 0;
+          const int parent = PB_IN_BOUNDS((e >> 16) & 0xFFF, PARENTS) ? (e >> 16) & 0xFFF : 0;
           Pos q = tile_parent(sh, parent);
           u32 k;
           if (c < clean_here) { /* quiet move off every line that matters: replies = base + pawns + king */
@@ -1037,7 +1039,7 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
             out.moves[out_base + w + c] = (u16)e;
             continue;
           }
-          const int parent = (e >> 16) & 0xFFF;
+          const int parent = PB_IN_BOUNDS((e >> 16) & 0xFFF, PARENTS) ? (e >> 16) & 0xFFF : 0;
           Pos q = tile_parent(sh, parent);
           make_move_kind<-1, false, true>(q, tb, (u16)(e & 0xFFFF), (int)(e >> 28)); /* == make_move, without the piece lookup */
           const size_t o = (size_t)(out_base + w + c);

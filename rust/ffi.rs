@@ -66,6 +66,7 @@ extern "C" {
     pub fn pabi_cuda_destroy(ctx: *mut Ctx);
     pub fn pabi_cuda_last_error(ctx: *mut Ctx) -> *const c_char;
     pub fn pabi_cuda_device(ctx: *const Ctx) -> i32;
+    pub fn pabi_cuda_bounds_violation(ctx: *mut Ctx) -> i32; // checking builds only; -1 in the shipped build
     pub fn pabi_cuda_host_alloc(bytes: usize, out: *mut *mut std::ffi::c_void) -> i32;
     pub fn pabi_cuda_host_free(ptr: *mut std::ffi::c_void);
 

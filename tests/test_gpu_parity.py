@@ -593,3 +593,10 @@ def test_device_side_workload_generators_reproduce_the_oracle_workloads(pb, engi
     assert engine.perft_batch(book, 4).tolist() == fx["book"]["perft"]
     positions = W.playout_positions(engine, 1_000_000)
     assert hashlib.sha256(positions.tobytes()).hexdigest() == fx["playouts"]["sha256"]
+
+
+def test_no_index_left_its_array_in_a_checking_build(pb, engine, small_engine):
+    """With the -DPABI_BOUNDS library in place (tools/bounds_suite.sh) every record and pool index of every kernel launched
+    by the tests above was range-checked; the shipped build answers -1 (no checks compiled in).  Runs last in this file."""
+    for e in (engine, small_engine):
+        assert e.bounds_violation() in (0, -1), f"out-of-range index at chess.cuh/kernels.cuh line {e.bounds_violation()}"
