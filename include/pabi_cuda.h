@@ -142,9 +142,12 @@ int pabi_cuda_perft_batch(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size
 int pabi_cuda_perft_batch_depths(pabi_cuda_ctx* ctx, const pabi_position_t* roots, const uint8_t* depths, size_t n,
                                  uint64_t* nodes_out, pabi_timing_t* timing);
 /* Root-subtree sharding for multi-GPU runs: the tree is expanded breadth-first to
- * `split_ply` plies (fewer if the depth is smaller), this call then walks only
- * the subtrees whose index in that frontier is congruent to shard_index modulo
- * shard_count.  Summing *nodes over all shards gives perft(root, depth). */
+ * `split_ply` plies (at most depth - 1), this call then walks only the subtrees of
+ * that frontier that belong to shard `shard_index` of `shard_count`.  A subtree's
+ * shard is a hash of its root record modulo shard_count, i.e. a property of the
+ * position, not of its place in the frontier: every rank can expand the top of the
+ * tree on its own, in any order, and the shards are still disjoint and exhaustive.
+ * Summing *nodes over all shards gives perft(root, depth). */
 int pabi_cuda_perft_shard(pabi_cuda_ctx* ctx, const pabi_position_t* root, uint8_t depth,
                           uint32_t split_ply, uint32_t shard_index, uint32_t shard_count,
                           uint64_t* nodes, pabi_timing_t* timing);

@@ -13,6 +13,7 @@
  * There is no CPU implementation of move generation in this library: without a
  * CUDA device every entry point here fails with the CUDA error code.
  */
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -34,6 +35,9 @@ namespace {
 
 constexpr size_t DEFAULT_CAPACITY = size_t(32) << 20; /* records per level buffer */
 constexpr int MAX_LEVELS = 24;
+constexpr int FAST_SLOTS = 2048;      /* device-sized frontiers per call (one counter each); the last slot is the overflow flag */
+constexpr size_t BRANCH_ESTIMATE = 32; /* children per position assumed when a frontier's size is only known on the device */
+constexpr size_t BRANCH_MARGIN = 4;   /* a ply is expanded without its exact size only if 4 x the estimate still fits the next buffer */
 
 struct Level {
   u64* rec = nullptr;
@@ -76,6 +80,16 @@ struct pabi_cuda_ctx {
   u32* d_bad_roots = nullptr;      /* k_pack: records that are not positions (replaced by bare kings, the call fails) */
   u32* h_bad_roots = nullptr;      /* pinned copy, valid after the call's final synchronisation */
   std::set<const void*> big_smem;  /* tile-kernel instantiations whose dynamic shared-memory limit has been raised */
+  /* frontier sizes that exist only on the device ("levels sized on the device"): one 64-bit counter per
+   * device-sized frontier of a call, FAST_SLOTS - 1 the overflow flag; read back once, when the call ends */
+  unsigned long long* d_fast = nullptr;
+  unsigned long long* h_fast = nullptr; /* pinned */
+  int fast_used = 0;                    /* counters handed out in this call */
+  std::vector<int> fast_interior, fast_leaf; /* counters whose frontier was expanded / was the input of K2 (statistics) */
+  bool exact_only = false;              /* this call walks on the exact path (a speculative walk overflowed, or PABI_EXACT_LEVELS=1) */
+  bool force_exact = false;
+  uint32_t shard_index = 0, shard_count = 1; /* this call keeps the subtrees of one shard ... */
+  int shard_level = -1;                      /* ... cut at this level (-1: no sharding) */
   Level levels[MAX_LEVELS];
   Level spare; /* shard gather target */
   Level merge_level; /* compaction target of merge_transpositions */
@@ -233,8 +247,9 @@ void launch_leaf_acc(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n, 
   else launch_tile_cfg<TILE_LEAF, SINGLE_ROOT, CFG>(ctx, in, 0, n, nullptr, out);
 }
 
-/* K2: the last two plies below the n records of `in` */
-void launch_leaf(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n) {
+/* K2: the last two plies below the n records of `in`.  With n_dev the true size is *n_dev (on the device) and n is the
+ * estimate the launch geometry is chosen for. */
+void launch_leaf(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n, const unsigned long long* n_dev = nullptr) {
   while (ctx->leaf_events.size() < 2 * (ctx->leaf_launches + 1)) {
     cudaEvent_t e;
     CK(cudaEventCreate(&e));
@@ -242,7 +257,8 @@ void launch_leaf(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n) {
   }
   CK(cudaEventRecord(ctx->leaf_events[2 * ctx->leaf_launches], ctx->stream));
   CK(cudaMemsetAsync(ctx->d_visited + 1, 0, sizeof(unsigned long long), ctx->stream)); /* the tile ticket counter */
-  const TileOut out{Frontier{nullptr, nullptr, 0, nullptr}, nullptr, nullptr, ctx->d_nodes, ctx->d_visited, ctx->d_visited + 1};
+  TileOut out{Frontier{nullptr, nullptr, 0, nullptr}, nullptr, nullptr, ctx->d_nodes, ctx->d_visited, ctx->d_visited + 1};
+  out.n_in = n_dev;
   /* below one default tile per thread group of the grid the frontier is cut into shorter tiles (measured: 197 281
    * parents are still faster with 256-parent tiles, 97 862 with 64-parent ones) */
   const size_t groups = (size_t)ctx->sm_count * TileDefault::GROUPS;
@@ -269,7 +285,25 @@ void launch_leaf(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n) {
   }
   CK(cudaEventRecord(ctx->leaf_events[2 * ctx->leaf_launches + 1], ctx->stream));
   ++ctx->leaf_launches;
-  ctx->leaf_parents += n;
+  if (!n_dev) ctx->leaf_parents += n; /* device-sized frontiers are added when their counters are read back */
+}
+
+/* K1 without a sizing pass (TILE_EXPAND_ATOMIC): the children of the records of `in` (n of them, or *n_dev) go to
+ * `children` in no particular order; their number is accumulated in *n_out (zeroed at the start of the call). */
+template <class CFG>
+void launch_expand_atomic_acc(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n, const TileOut& out) {
+  if (acc == PER_ROOT) launch_tile_cfg<TILE_EXPAND_ATOMIC, PER_ROOT, CFG>(ctx, in, 0, n, nullptr, out);
+  else launch_tile_cfg<TILE_EXPAND_ATOMIC, SINGLE_ROOT, CFG>(ctx, in, 0, n, nullptr, out);
+}
+
+void launch_expand_atomic(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n, const unsigned long long* n_dev, Frontier children,
+                          size_t children_cap, unsigned long long* n_out) {
+  TileOut out{children, nullptr, nullptr, nullptr, nullptr, nullptr};
+  out.n_in = n_dev, out.n_out = n_out, out.overflow = ctx->d_fast + FAST_SLOTS - 1, out.out_cap = children_cap;
+  const size_t groups = (size_t)ctx->sm_count * TileDefault::GROUPS;
+  if (n < groups * TileSmall::PARENTS) launch_expand_atomic_acc<TileTiny>(ctx, acc, in, n, out);
+  else if (n < groups * TileDefault::PARENTS) launch_expand_atomic_acc<TileSmall>(ctx, acc, in, n, out);
+  else launch_expand_atomic_acc<TileDefault>(ctx, acc, in, n, out);
 }
 
 /* K1: children of records [first, first + n) of `in`, at the offsets of `prefix` (count_and_scan) */
@@ -369,38 +403,96 @@ int root_levels(pabi_cuda_ctx* ctx, int lv, size_t& n, int max_plies, Accounting
   return (int)ctx->h_result[0];
 }
 
-void descend(pabi_cuda_ctx* ctx, int lv, size_t n, int remaining, Accounting acc) {
+/* A frontier and what the host knows about its size: `n` records when `n_dev` is null; otherwise the truth is *n_dev, on
+ * the device, and n is an estimate that only shapes the launches (every kernel walks its input with a stride or a ticket
+ * counter, so any grid covers any size). */
+struct Sized {
+  size_t n;
+  const unsigned long long* n_dev;
+};
+
+struct Redo {}; /* a speculative ply did not fit its buffer: the call is repeated on the exact path */
+
+unsigned long long* fast_counter(pabi_cuda_ctx* ctx) { /* a zeroed device counter for one device-sized frontier; null when used up */
+  if (ctx->fast_used >= FAST_SLOTS - 1) return nullptr;
+  return ctx->d_fast + ctx->fast_used++;
+}
+
+/* the exact size of a device-sized frontier: the one place where the host waits in the middle of a walk */
+size_t exact_size(pabi_cuda_ctx* ctx, const Sized& s) {
+  if (!s.n_dev) return s.n;
+  const size_t slot = (size_t)(s.n_dev - ctx->d_fast);
+  CK(cudaMemcpyAsync(ctx->h_fast + slot, s.n_dev, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_fast + FAST_SLOTS - 1, ctx->d_fast + FAST_SLOTS - 1, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_fast[FAST_SLOTS - 1]) throw Redo{};
+  return (size_t)ctx->h_fast[slot];
+}
+
+void descend(pabi_cuda_ctx* ctx, int lv, Sized s, int remaining, Accounting acc, bool arrived);
+
+/* Root-subtree sharding (pabi_cuda_perft_shard): when the walk arrives at the split level with a fresh set of records, only
+ * those of this call's shard go on (k_filter_shard: a partition by content, independent of the records' order). */
+void keep_my_shard(pabi_cuda_ctx* ctx, int lv, Sized& s) {
+  alloc_level(ctx, ctx->spare, ctx->capacity);
+  unsigned long long* kept = ctx->exact_only ? nullptr : fast_counter(ctx);
+  const bool on_device = kept != nullptr;
+  if (!kept) {
+    kept = (unsigned long long*)ctx->d_result + 3;
+    CK(cudaMemsetAsync(kept, 0, sizeof(u64), ctx->stream));
+  }
+  k_filter_shard<<<grid_for(ctx, s.n, 256, 8), 256, 0, ctx->stream>>>(frontier_of(ctx->levels[lv]), s.n, s.n_dev, ctx->shard_index,
+                                                                      ctx->shard_count, frontier_of(ctx->spare), kept);
+  LAUNCHED();
+  std::swap(ctx->levels[lv], ctx->spare);
+  if (on_device) {
+    s = Sized{s.n / ctx->shard_count + 1, kept};
+  } else {
+    CK(cudaMemcpyAsync(ctx->h_result + 3, kept, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    s = Sized{(size_t)ctx->h_result[3], nullptr};
+  }
+}
+
+void count_level(pabi_cuda_ctx* ctx, int lv, const Sized& s, Accounting acc) { /* one ply left: position.rs:914-916 */
+  Level& cur = ctx->levels[lv];
+  const int grid = grid_for(ctx, s.n, FLAT_THREADS, 4);
+  if (acc == PER_ROOT)
+    k_count_accumulate<PER_ROOT><<<grid, FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, frontier_of(cur), s.n, s.n_dev, ctx->d_nodes);
+  else if (acc == WEIGHTED)
+    k_count_accumulate<WEIGHTED><<<grid, FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, frontier_of(cur), s.n, s.n_dev, ctx->d_nodes);
+  else
+    k_count_accumulate<SINGLE_ROOT><<<grid, FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, frontier_of(cur), s.n, s.n_dev, ctx->d_nodes);
+  LAUNCHED();
+}
+
+void note_size(pabi_cuda_ctx* ctx, const Sized& s, bool leaf_input) { /* statistics of a frontier that is being walked */
+  if (!s.n_dev) {
+    ctx->interior += s.n;
+    return;
+  }
+  const int slot = (int)(s.n_dev - ctx->d_fast);
+  ctx->fast_interior.push_back(slot);
+  if (leaf_input) ctx->fast_leaf.push_back(slot);
+}
+
+/* The exact path: count -> scan -> expand with the children in the reference's move order; a level whose children would
+ * not fit the next buffer is cut into chunks, each finished depth-first before the next starts. */
+void descend_exact(pabi_cuda_ctx* ctx, int lv, size_t n, int remaining, Accounting acc) {
   if (n == 0) return;
-  if (remaining > 2) { /* the launch-bound top of the tree: several plies per launch, two are left for K2 */
+  if (remaining > 2 && ctx->exact_only) { /* the launch-bound top of the tree: several plies per launch, two are left for K2 */
     size_t below = n;
-    const int plies = root_levels(ctx, lv, below, remaining - 2, acc);
+    const int plies = root_levels(ctx, lv, below, std::min(remaining - 2, ctx->shard_level > lv ? ctx->shard_level - lv : remaining), acc);
     if (plies) {
-      descend(ctx, lv + plies, below, remaining - plies, acc);
+      descend(ctx, lv + plies, Sized{below, nullptr}, remaining - plies, acc, true);
       return;
     }
-  }
-  ctx->interior += n;
-  if (remaining == 1) {
-    Level& cur = ctx->levels[lv];
-    const int grid = grid_for(ctx, n, FLAT_THREADS, 4);
-    if (acc == PER_ROOT)
-      k_count_accumulate<PER_ROOT><<<grid, FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, frontier_of(cur), n, ctx->d_nodes);
-    else if (acc == WEIGHTED)
-      k_count_accumulate<WEIGHTED><<<grid, FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, frontier_of(cur), n, ctx->d_nodes);
-    else
-      k_count_accumulate<SINGLE_ROOT><<<grid, FLAT_THREADS, FLAT_SMEM, ctx->stream>>>(ctx->dt, frontier_of(cur), n, ctx->d_nodes);
-    LAUNCHED();
-    return;
-  }
-  if (remaining == 2) {
-    launch_leaf(ctx, acc, frontier_of(ctx->levels[lv]), n);
-    /* the children are generated and counted inside the kernel */
-    return;
   }
   if (lv + 1 >= MAX_LEVELS) {
     ctx->error = "perft depth exceeds the supported number of breadth-first levels";
     throw CudaFail{cudaErrorInvalidValue};
   }
+  ctx->interior += n;
   alloc_level(ctx, ctx->levels[lv + 1], ctx->capacity);
   if (acc == WEIGHTED) ensure_mult(ctx, ctx->levels[lv + 1]);
   {
@@ -409,7 +501,7 @@ void descend(pabi_cuda_ctx* ctx, int lv, size_t n, int remaining, Accounting acc
   }
   size_t start = 0;
   while (start < n) {
-    /* levels may have been swapped by a deeper merge_transpositions: re-read them every time */
+    /* levels may have been swapped by a deeper merge_transpositions or shard filter: re-read them every time */
     Level& cur = ctx->levels[lv];
     Level& next = ctx->levels[lv + 1];
     size_t end = n, children = 0;
@@ -435,10 +527,49 @@ void descend(pabi_cuda_ctx* ctx, int lv, size_t n, int remaining, Accounting acc
     if (children) {
       launch_expand(ctx, acc, frontier_of(cur), start, end - start, cur.prefix, frontier_of(next));
       if (acc == WEIGHTED) children = merge_transpositions(ctx, lv + 1, children);
-      descend(ctx, lv + 1, children, remaining - 1, acc);
+      descend(ctx, lv + 1, Sized{children, nullptr}, remaining - 1, acc, true);
     }
     start = end;
   }
+}
+
+/* Walks `remaining` plies below the records of level `lv`, adding leaf counts to d_nodes (per root for PER_ROOT; times the
+ * record's multiplicity for WEIGHTED, where every expanded chunk is passed through merge_transpositions).
+ *
+ * Small plies are expanded WITHOUT the host learning their size (TILE_EXPAND_ATOMIC: the next frontier's size is a counter on
+ * the device, the following launch reads it): the launch-bound part of a walk runs without a single host round trip.  A ply
+ * is taken this way only while four times the estimated number of children still fits the next buffer; when the estimate
+ * gets large the host fetches the exact size (exact_size) and continues on the exact, chunking path, where a round trip is
+ * negligible.  Should a speculative ply overflow all the same, its kernel raises a flag and the call is redone exactly. */
+void descend(pabi_cuda_ctx* ctx, int lv, Sized s, int remaining, Accounting acc, bool arrived) {
+  if (!s.n_dev && s.n == 0) return;
+  if (arrived && lv == ctx->shard_level && ctx->shard_count > 1) {
+    keep_my_shard(ctx, lv, s);
+    if (!s.n_dev && s.n == 0) return;
+  }
+  if (remaining == 1) {
+    note_size(ctx, s, false);
+    count_level(ctx, lv, s, acc);
+    return;
+  }
+  const bool split_below = ctx->shard_count > 1 && ctx->shard_level > lv; /* the shard is cut at a deeper ply: K2 must not pass over it */
+  if (remaining == 2 && !split_below) { /* the children are generated and counted inside K2 */
+    note_size(ctx, s, true);
+    launch_leaf(ctx, acc, frontier_of(ctx->levels[lv]), s.n, s.n_dev);
+    return;
+  }
+  unsigned long long* n_children = nullptr;
+  const bool speculate = !ctx->exact_only && acc != WEIGHTED && lv + 1 < MAX_LEVELS &&
+                         s.n * BRANCH_ESTIMATE * BRANCH_MARGIN <= ctx->capacity && (n_children = fast_counter(ctx)) != nullptr;
+  if (!speculate) {
+    descend_exact(ctx, lv, exact_size(ctx, s), remaining, acc);
+    return;
+  }
+  alloc_level(ctx, ctx->levels[lv + 1], ctx->capacity);
+  note_size(ctx, s, false);
+  launch_expand_atomic(ctx, acc, frontier_of(ctx->levels[lv]), s.n, s.n_dev, frontier_of(ctx->levels[lv + 1]), ctx->levels[lv + 1].cap,
+                       n_children);
+  descend(ctx, lv + 1, Sized{s.n * BRANCH_ESTIMATE, n_children}, remaining - 1, acc, true);
 }
 
 struct CallTimer {
@@ -523,60 +654,42 @@ int perft_impl(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, int d
       CK(cudaMemcpyAsync(ctx->levels[0].mult, &one, sizeof one, cudaMemcpyHostToDevice, ctx->stream));
     }
     timer.begin_device();
-    CK(cudaMemsetAsync(ctx->d_nodes, 0, n_out * sizeof(unsigned long long), ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_visited, 0, sizeof(unsigned long long), ctx->stream));
-    if (shard_count <= 1) {
-      descend(ctx, 0, n, depth, acc);
-    } else {
-      /* breadth-first to the split ply (at most depth - 1 so that one ply is left), whole levels only */
-      int remaining = depth;
-      int lv = 0;
-      size_t cnt = n;
-      int plies = (int)split_ply;
-      if (plies > depth - 1) plies = depth - 1;
-      for (int s = 0; s < plies && cnt; s++) {
-        {
-          size_t below = cnt;
-          const int done = root_levels(ctx, lv, below, plies - s, acc);
-          if (done) {
-            cnt = below, lv += done, remaining -= done, s += done - 1;
-            continue;
-          }
+    /* root-subtree sharding: the walk keeps one shard of the frontier at the split ply (at most depth - 1, so that a ply is left) */
+    ctx->shard_index = shard_index, ctx->shard_count = shard_count ? shard_count : 1;
+    ctx->shard_level = shard_count > 1 ? (int)std::min<uint32_t>(split_ply, (uint32_t)depth - 1) : -1;
+    for (int attempt = 0;; attempt++) {
+      ctx->exact_only = ctx->force_exact || attempt > 0;
+      ctx->fast_used = 0, ctx->fast_interior.clear(), ctx->fast_leaf.clear();
+      ctx->interior = 0, ctx->leaf_parents = 0, ctx->leaf_launches = 0;
+      CK(cudaMemsetAsync(ctx->d_nodes, 0, n_out * sizeof(unsigned long long), ctx->stream));
+      CK(cudaMemsetAsync(ctx->d_visited, 0, sizeof(unsigned long long), ctx->stream));
+      if (!ctx->exact_only) CK(cudaMemsetAsync(ctx->d_fast, 0, FAST_SLOTS * sizeof(u64), ctx->stream));
+      bool redo = false;
+      try {
+        descend(ctx, 0, Sized{n, nullptr}, depth, acc, true);
+      } catch (const Redo&) {
+        redo = true;
+      }
+      if (!redo) {
+        timer.end_device();
+        CK(cudaMemcpyAsync(nodes_out, ctx->d_nodes, n_out * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_result + 2, ctx->d_visited, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        if (ctx->fast_used) { /* the sizes of the device-sized frontiers and the overflow flag, in the same round trip */
+          CK(cudaMemcpyAsync(ctx->h_fast, ctx->d_fast, ctx->fast_used * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+          CK(cudaMemcpyAsync(ctx->h_fast + FAST_SLOTS - 1, ctx->d_fast + FAST_SLOTS - 1, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
         }
-        if (lv + 1 >= MAX_LEVELS) {
-          ctx->error = "split_ply exceeds the supported number of breadth-first levels";
-          throw CudaFail{cudaErrorInvalidValue};
-        }
-        Level& cur = ctx->levels[lv];
-        Level& next = ctx->levels[lv + 1];
-        count_and_scan(ctx, cur.rec, cur.cap, 0, cnt, cur.counts, cur.prefix);
-        CK(cudaMemcpyAsync(ctx->h_result, cur.prefix + cnt, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        const size_t children = (size_t)ctx->h_result[0];
-        if (children > ctx->capacity) {
-          ctx->error = "split_ply frontier exceeds the frontier capacity";
-          throw CudaFail{cudaErrorInvalidValue};
-        }
-        alloc_level(ctx, next, ctx->capacity);
-        if (children) launch_expand(ctx, acc, frontier_of(cur), 0, cnt, cur.prefix, frontier_of(next));
-        ctx->interior += cnt;
-        cnt = children, ++lv, --remaining;
+        redo = ctx->fast_used && ctx->h_fast[FAST_SLOTS - 1] != 0;
       }
-      /* keep every shard_count-th subtree */
-      const size_t mine = cnt > shard_index ? (cnt - shard_index + shard_count - 1) / shard_count : 0;
-      if (mine) {
-        alloc_level(ctx, ctx->spare, ctx->capacity);
-        k_gather_shard<<<grid_for(ctx, mine, 256, 8), 256, 0, ctx->stream>>>(frontier_of(ctx->levels[lv]), mine, shard_index,
-                                                                            shard_count, frontier_of(ctx->spare));
-        LAUNCHED();
-        std::swap(ctx->levels[lv], ctx->spare);
-        descend(ctx, lv, mine, remaining, acc);
+      if (!redo) break;
+      if (attempt > 0) {
+        ctx->error = "the exact path reported an overflow";
+        throw CudaFail{cudaErrorUnknown};
       }
+      if (acc == WEIGHTED) ctx->merged_away = 0;
     }
-    timer.end_device();
-    CK(cudaMemcpyAsync(nodes_out, ctx->d_nodes, n_out * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_result + 2, ctx->d_visited, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    for (int slot : ctx->fast_interior) ctx->interior += ctx->h_fast[slot];
+    for (int slot : ctx->fast_leaf) ctx->leaf_parents += ctx->h_fast[slot];
     ctx->interior += ctx->h_result[2];
     /* every node of plies 1..d-1 written once and read once at 64 B */
     timer.finish(timing, 2 * 64 * (ctx->interior > n ? ctx->interior - n : 0));
@@ -623,6 +736,9 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     ctx->dt.g.rook_attacks = ctx->d_rook;
     ctx->dt.g.rays = ctx->d_rays;
     ctx->dt.g.zobrist = ctx->d_zobrist;
+    CK(cudaMalloc(&ctx->d_fast, FAST_SLOTS * sizeof(u64)));
+    CK(cudaMallocHost(&ctx->h_fast, FAST_SLOTS * sizeof(u64)));
+    if (const char* v = std::getenv("PABI_EXACT_LEVELS")) ctx->force_exact = std::atoi(v) != 0; /* no speculative plies (comparison runs) */
     CK(cudaMalloc(&ctx->d_bad_roots, sizeof(u32)));
     CK(cudaMallocHost(&ctx->h_bad_roots, sizeof(u32)));
     *ctx->h_bad_roots = 0;
@@ -685,6 +801,8 @@ void pabi_cuda_destroy(pabi_cuda_ctx* ctx) {
   if (ctx->d_rays) cudaFree(ctx->d_rays);
   if (ctx->d_zobrist) cudaFree(ctx->d_zobrist);
   if (ctx->d_bad_roots) cudaFree(ctx->d_bad_roots);
+  if (ctx->d_fast) cudaFree(ctx->d_fast);
+  if (ctx->h_fast) cudaFreeHost(ctx->h_fast);
   if (ctx->h_bad_roots) cudaFreeHost(ctx->h_bad_roots);
   for (cudaEvent_t e : ctx->leaf_events) cudaEventDestroy(e);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);

@@ -167,8 +167,10 @@ k_count(DeviceTables dt, const u64* __restrict__ rec, size_t stride, size_t firs
 /* perft with one ply left: nodes[root] += generate_moves().len() (position.rs:914-916) */
 template <Accounting ACC>
 __global__ void __launch_bounds__(FLAT_THREADS)
-k_count_accumulate(DeviceTables dt, Frontier f, size_t n, unsigned long long* __restrict__ nodes) {
+k_count_accumulate(DeviceTables dt, Frontier f, size_t n, const unsigned long long* __restrict__ n_in, unsigned long long* __restrict__ nodes) {
   constexpr bool MULTI_ROOT = ACC == PER_ROOT;
+  if (n_in) n = (size_t)*n_in; /* a frontier sized on the device */
+  if ((size_t)blockIdx.x * FLAT_THREADS >= n) return;
   extern __shared__ __align__(16) unsigned char smem[];
   SharedTables* st = reinterpret_cast<SharedTables*>(smem);
   __shared__ u64 red[FLAT_THREADS / 32];
@@ -510,12 +512,44 @@ k_games_play_random(DeviceTables dt, GamesState gs, const u64* __restrict__ seed
   }
 }
 
-/* every shard_count-th record starting at shard_index (root-subtree sharding) */
-__global__ void k_gather_shard(Frontier in, size_t n_out, u32 shard_index, u32 shard_count, Frontier out) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t src = (size_t)shard_index + i * shard_count;
-    store_pos(out.rec, out.stride, i, load_pos(in.rec, in.stride, src));
-    if (out.roots) out.roots[i] = in.roots ? in.roots[src] : 0;
+/* Root-subtree sharding: the records of a frontier whose content hash is congruent to shard_index modulo shard_count.
+ * The partition depends on the records only, not on their order in the frontier, so ranks that each expanded the tree
+ * themselves (children land in no fixed order, TILE_EXPAND_ATOMIC) still pick disjoint, exhaustive shards.  Compaction
+ * with one warp-aggregated atomicAdd per warp; *n_out is the shard's size. */
+PB_HD u64 shard_hash(const Pos& p) {
+  u64 h = 0x9E3779B97F4A7C15ULL;
+  const u64 words[8] = {p.white, p.pawns, p.knights, p.bishops, p.rooks, p.queens, p.kings, p.meta};
+  for (int i = 0; i < 8; i++) {
+    h = (h ^ words[i]) * 0xBF58476D1CE4E5B9ULL;
+    h ^= h >> 29;
+  }
+  h *= 0x94D049BB133111EBULL;
+  return h ^ (h >> 32);
+}
+
+__global__ void k_filter_shard(Frontier in, size_t n, const unsigned long long* __restrict__ n_in, u32 shard_index, u32 shard_count,
+                               Frontier out, unsigned long long* __restrict__ n_out) {
+  if (n_in) n = (size_t)*n_in;
+  const size_t rounds = (n + (size_t)gridDim.x * blockDim.x - 1) / ((size_t)gridDim.x * blockDim.x);
+  for (size_t r = 0; r < rounds; r++) { /* whole warps stay in the loop: the ballot below needs every lane */
+    const size_t i = (r * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    Pos p;
+    bool keep = false;
+    if (i < n) {
+      p = load_pos(in.rec, in.stride, i);
+      keep = shard_hash(p) % shard_count == shard_index;
+    }
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, keep);
+    if (!mask) continue;
+    const int lane = threadIdx.x & 31, leader = __ffs((int)mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(n_out, (unsigned long long)__popc(mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (keep) {
+      const size_t o = (size_t)base + __popc(mask & ((1u << lane) - 1));
+      store_pos(out.rec, out.stride, o, p);
+      if (out.roots) out.roots[o] = in.roots ? in.roots[i] : 0;
+    }
   }
 }
 
@@ -876,7 +910,11 @@ __device__ __forceinline__ Pos tile_parent(const TileGroupShared<CFG>& sh, int k
 enum TileMode {
   TILE_LEAF,   /* K2: count the children, write nothing */
   TILE_EXPAND, /* K1: write the children as SoA records */
-  TILE_MOVES   /* K3: write the moves themselves (u16, CSR) */
+  TILE_MOVES,  /* K3: write the moves themselves (u16, CSR) */
+  TILE_EXPAND_ATOMIC /* K1 without a sizing pass: a tile counts its own parents, scans the counts inside the thread group and
+                        reserves its children's range with ONE atomicAdd on the next level's record counter.  The children of a
+                        ply land in no particular tile order (perft does not care), there is no k_count / k_scan_* launch, and the
+                        size of the next frontier exists only on the device: the host does not synchronise between plies */
 };
 
 struct TileOut {
@@ -886,6 +924,12 @@ struct TileOut {
   unsigned long long* nodes;        /* TILE_LEAF: per-root (or single) leaf counts */
   unsigned long long* visited;      /* TILE_LEAF statistics: children generated */
   unsigned long long* ticket;       /* TILE_LEAF: tiles are handed out dynamically (zeroed before the launch) */
+  /* frontier sizes that live on the device (the host does not wait for a ply to learn how large the next one is): */
+  const unsigned long long* n_in;   /* when set, the number of input records is *n_in, not the launch argument */
+  unsigned long long* n_out;        /* TILE_EXPAND_ATOMIC: the children's record counter (zeroed before the launch) */
+  unsigned long long* overflow;     /* TILE_EXPAND_ATOMIC: set when a tile's children would not fit out_cap (the host then redoes
+                                       the call on the exact, chunked path) */
+  size_t out_cap;
 };
 
 /* K2's enumerate_split sink, DirectEmitter, lives in incremental.cuh (host-checkable). */
@@ -900,6 +944,9 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
   constexpr int PARENTS = CFG::PARENTS, POOL = CFG::POOL, GROUPS = CFG::GROUPS, GT = CFG::GROUP_THREADS;
   constexpr int SYNC = GROUPS == 1 ? 0 : GT; /* 0: plain __syncthreads */
   constexpr bool LEAF = MODE == TILE_LEAF;
+  constexpr bool ATOMIC = MODE == TILE_EXPAND_ATOMIC;
+  if (out.n_in) n = (size_t)*out.n_in; /* a frontier sized on the device: the grid was launched for an upper bound */
+  if ((size_t)blockIdx.x * GROUPS * PARENTS >= n) return; /* no tile for this block (the same for all its threads) */
   extern __shared__ __align__(16) unsigned char smem[];
   TileShared<CFG>& block = *reinterpret_cast<TileShared<CFG>*>(smem);
   stage_tables(&block.tables, dt.image);
@@ -1003,8 +1050,24 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
       sh.parents[0][tid] = p.white, sh.parents[1][tid] = p.pawns, sh.parents[2][tid] = p.knights;
       sh.parents[3][tid] = p.bishops, sh.parents[4][tid] = p.rooks, sh.parents[5][tid] = p.queens;
       sh.parents[6][tid] = p.kings, sh.parents[7][tid] = p.meta;
+      if (ATOMIC) cnt = count_moves(p, tb);
     }
-    {
+    if (ATOMIC) {
+      /* sizes from the tile itself: scan of the parents' counts inside the thread group, then one reservation */
+      off = block_exclusive_scan<GT, SYNC, u32>(cnt, reinterpret_cast<u32*>(sh.warp_sums), total, tid, group);
+      if (tid == 0) {
+        unsigned long long base = total ? atomicAdd(out.n_out, (unsigned long long)total) : 0ULL;
+        if (base + total > out.out_cap) {
+          atomicExch(out.overflow, 1ULL);
+          base = ~0ULL;
+        }
+        sh.next_tile = base;
+      }
+      group_sync<SYNC>(group);
+      out_base = sh.next_tile;
+      group_sync<SYNC>(group); /* thread 0 writes next_tile again in the next tile */
+      if (out_base == ~0ULL) continue; /* the same for the whole group */
+    } else {
       const size_t tile_first = first + tile * PARENTS;
       const size_t tile_end = first + min((tile + 1) * (size_t)PARENTS, n);
       const u64 tile_prefix = prefix[tile_first];
@@ -1087,6 +1150,7 @@ struct LeafWarpBlock {
 template <Accounting ACC>
 __global__ void __launch_bounds__(LEAFW_THREADS, 1)
 k_leaf_warp(DeviceTables dt, Frontier in, size_t n, TileOut out) {
+  if (out.n_in) n = (size_t)*out.n_in; /* a frontier sized on the device */
   extern __shared__ __align__(16) unsigned char smem[];
   LeafWarpBlock& block = *reinterpret_cast<LeafWarpBlock*>(smem);
   stage_tables(&block.tables, dt.image);

@@ -140,7 +140,7 @@ def test_perft_batch_chunked(small_engine, playout_positions):
 
 def test_shards_sum_to_the_whole(pb, engine):
     p = pb.Position.from_fen(KIWIPETE)
-    for depth, split in ((4, 1), (4, 2), (5, 2), (3, 5), (1, 2)):
+    for depth, split in ((4, 1), (4, 2), (5, 2), (3, 5), (1, 2), (2, 1), (3, 2), (4, 0)):
         whole = engine.perft(p, depth)
         for count in (1, 2, 3, 8):
             assert sum(engine.perft_shard(p, depth, split, i, count) for i in range(count)) == whole
@@ -600,3 +600,16 @@ def test_no_index_left_its_array_in_a_checking_build(pb, engine, small_engine):
     by the tests above was range-checked; the shipped build answers -1 (no checks compiled in).  Runs last in this file."""
     for e in (engine, small_engine):
         assert e.bounds_violation() in (0, -1), f"out-of-range index at chess.cuh/kernels.cuh line {e.bounds_violation()}"
+
+
+def test_speculative_plies_fall_back_to_the_exact_path_when_a_buffer_overflows(pb):
+    """Small plies are expanded without the host knowing their size, on the estimate of 32 children per position; a ply that
+    does not fit after all raises the overflow flag and the call is redone on the exact, chunking path.  A 4 096-record
+    frontier and a position with ~120 moves per node force exactly that."""
+    dense = pb.Position.try_from("knq5/ppQ1qQQ1/2q4q/5Q2/1Q1Q3q/2qQ3q/Q4qPP/q1Q3NK w - - 0 1")
+    tiny = pb.Engine(0, frontier_capacity=4096)
+    assert tiny.perft(dense, 3) == 1664938
+    assert tiny.perft(dense, 4) == 169711264
+    assert sum(tiny.perft_shard(dense, 4, 2, i, 3) for i in range(3)) == 169711264
+    assert tiny.perft(pb.Position.starting(), 6) == 119060324
+    tiny.close()
