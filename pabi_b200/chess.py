@@ -212,6 +212,22 @@ class Engine:
         self.last_timing = t
         return offsets[: n + 1], moves[: int(offsets[n])]
 
+    def pack_records(self, positions, device_records: int, stride: int) -> None:
+        """Positions -> 64-byte SoA records at a device address (`pabi_cuda_pack_records`): word w of record i at
+        device_records[w * stride + i]."""
+        arr = _as_array(positions)
+        self._check(_native.lib().pabi_cuda_pack_records(self._ctx, arr.ctypes.data, len(arr), device_records, stride))
+
+    def generate_moves_resident(self, device_records: int, stride: int, n: int, device_offsets: int, device_moves: int,
+                                moves_cap: int) -> Tuple[int, Timing]:
+        """Move lists of records that already live on the device, written to device arrays (`pabi_cuda_generate_moves_device`):
+        returns (total moves, timing)."""
+        total, t = C.c_uint64(), Timing()
+        self._check(_native.lib().pabi_cuda_generate_moves_device(self._ctx, device_records, stride, n, device_offsets, device_moves,
+                                                                  moves_cap, C.byref(total), C.byref(t)))
+        self.last_timing = t
+        return total.value, t
+
     def count_moves_batch(self, positions) -> np.ndarray:
         arr = _as_array(positions)
         out, t = np.zeros(len(arr), dtype=np.uint32), Timing()

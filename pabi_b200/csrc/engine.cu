@@ -88,6 +88,14 @@ struct pabi_cuda_ctx {
   std::vector<int> fast_interior, fast_leaf; /* counters whose frontier was expanded / was the input of K2 (statistics) */
   bool exact_only = false;              /* this call walks on the exact path (a speculative walk overflowed, or PABI_EXACT_LEVELS=1) */
   bool force_exact = false;
+  /* move lists (K3 fused): a second and a third stream so that the copies of a batch overlap its kernels */
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  std::vector<cudaEvent_t> list_events; /* per chunk: positions on the device, kernel started, kernel finished */
+  unsigned long long* d_list_status = nullptr; /* one scan word per tile of a batch */
+  size_t list_status_cap = 0;
+  unsigned long long* h_list_totals = nullptr; /* pinned: moves up to the end of every chunk */
+  size_t list_totals_cap = 0;
+  bool list_two_pass = false; /* PABI_LIST_TWO_PASS=1: the round-1 path (k_count, k_scan_*, k_moves_warp), kept for comparison */
   uint32_t shard_index = 0, shard_count = 1; /* this call keeps the subtrees of one shard ... */
   int shard_level = -1;                      /* ... cut at this level (-1: no sharding) */
   Level levels[MAX_LEVELS];
@@ -322,6 +330,33 @@ void launch_expand(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t first
   if (ctx->tile_variant == 0 && n < groups * TileSmall::PARENTS) launch_expand_acc<TileTiny>(ctx, acc, in, first, n, prefix, out);
   else if (ctx->tile_variant == 0 && n < groups * TileDefault::PARENTS) launch_expand_acc<TileSmall>(ctx, acc, in, first, n, prefix, out);
   else launch_expand_acc<TileDefault>(ctx, acc, in, first, n, prefix, out);
+}
+
+/* K3 fused (k_moves_fused): tiles of a batch, its scan words, one launch over the tiles [t0, t1) */
+constexpr size_t LIST_TILE = 32;           /* positions per tile: one warp pass */
+#ifndef PABI_LIST_CHUNK_TILES
+#define PABI_LIST_CHUNK_TILES 2048
+#endif
+constexpr size_t LIST_CHUNK_TILES = PABI_LIST_CHUNK_TILES; /* 2048 tiles = 65 536 positions = 7.3 MB of records per copy: the copies set the pace (PCIe), so many small chunks keep the tail after the last copy short (measured on 1 M positions, page-locked arrays: 1024 tiles 3.59 ms, 2048 2.66, 4096 2.76, 8192 2.71) */
+size_t list_tiles(size_t n) { return (n + LIST_TILE - 1) / LIST_TILE; }
+
+void prepare_list_scan(pabi_cuda_ctx* ctx, size_t tiles) {
+  if (ctx->list_status_cap < tiles + 1) {
+    if (ctx->d_list_status) CK(cudaFree(ctx->d_list_status));
+    ctx->d_list_status = nullptr, ctx->list_status_cap = 0;
+    CK(cudaMalloc(&ctx->d_list_status, (tiles + 1025) * sizeof(u64)));
+    ctx->list_status_cap = tiles + 1024;
+  }
+  CK(cudaMemsetAsync(ctx->d_list_status, 0, (tiles + 1) * sizeof(u64), ctx->stream)); /* [tiles] is the ticket counter */
+}
+
+void launch_list_chunk(pabi_cuda_ctx* ctx, const ListInput& in, size_t n, size_t t0, size_t t1, u16* moves, size_t moves_cap, u32* offsets) {
+  unsigned long long* ticket = ctx->d_list_status + ctx->list_status_cap; /* the last word of the allocation */
+  CK(cudaMemsetAsync(ticket, 0, sizeof(u64), ctx->stream));
+  const ListScan scan{ctx->d_list_status, ticket, t0, t1};
+  const size_t blocks = std::min<size_t>((t1 - t0 + LIST_THREADS / 32 - 1) / (LIST_THREADS / 32), (size_t)ctx->sm_count);
+  k_moves_fused<<<(unsigned)blocks, LIST_THREADS, sizeof(ListShared), ctx->stream>>>(ctx->dt, in, n, scan, moves, moves_cap, offsets);
+  LAUNCHED();
 }
 
 /* K3: ordered move lists of records [0, n) at the offsets of `prefix`; the caller has checked the capacity */
@@ -759,6 +794,10 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     CK(cudaFuncSetAttribute(k_random_playouts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_leaf_warp<SINGLE_ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeafWarpBlock)));
     CK(cudaFuncSetAttribute(k_moves_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MovesShared)));
+    CK(cudaFuncSetAttribute(k_moves_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ListShared)));
+    CK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    if (const char* v = std::getenv("PABI_LIST_TWO_PASS")) ctx->list_two_pass = std::atoi(v) != 0;
     CK(cudaFuncSetAttribute(k_parse_fens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_games_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
     CK(cudaFuncSetAttribute(k_games_result, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));
@@ -766,6 +805,7 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     if (const char* v = std::getenv("PABI_TILE_VARIANT")) {
       ctx->tile_variant = std::atoi(v);
       if (ctx->tile_variant != 9 && ctx->tile_variant != 8 && (ctx->tile_variant < 0 || ctx->tile_variant >= TILE_VARIANTS)) ctx->tile_variant = 0;
+      if (ctx->tile_variant == 9) ctx->list_two_pass = true; /* the block-level K3 needs the scanned offsets */
     }
   } catch (const CudaFail& f) {
     std::fprintf(stderr, "pabi_cuda_create: %s\n", ctx->error.c_str());
@@ -805,6 +845,11 @@ void pabi_cuda_destroy(pabi_cuda_ctx* ctx) {
   if (ctx->h_fast) cudaFreeHost(ctx->h_fast);
   if (ctx->h_bad_roots) cudaFreeHost(ctx->h_bad_roots);
   for (cudaEvent_t e : ctx->leaf_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->list_events) cudaEventDestroy(e);
+  if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+  if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+  if (ctx->d_list_status) cudaFree(ctx->d_list_status);
+  if (ctx->h_list_totals) cudaFreeHost(ctx->h_list_totals);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1278,24 +1323,41 @@ int pabi_cuda_generate_moves_device(pabi_cuda_ctx* ctx, const uint64_t* device_r
   try {
     CK(cudaSetDevice(ctx->device));
     CallTimer timer(ctx);
-    u32* counts = (u32*)ensure(ctx, S_COUNTS, (n + 1) * sizeof(u32));
-    u64* prefix = (u64*)ensure(ctx, S_PREFIX, (n + 2) * sizeof(u64));
-    timer.begin_device();
-    if (n) {
-      count_and_scan(ctx, device_records, stride, 0, n, counts, prefix);
-      CK(cudaMemcpyAsync(ctx->h_result, prefix + n, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaStreamSynchronize(ctx->stream));
-      if (device_moves && ctx->h_result[0] <= moves_cap) {
-        launch_moves(ctx, device_records, stride, n, prefix, device_moves, device_offsets);
+    if (ctx->list_two_pass) { /* the round-1 path: sizing pass, scan, host round trip for the total, emitting pass */
+      u32* counts = (u32*)ensure(ctx, S_COUNTS, (n + 1) * sizeof(u32));
+      u64* prefix = (u64*)ensure(ctx, S_PREFIX, (n + 2) * sizeof(u64));
+      timer.begin_device();
+      if (n) {
+        count_and_scan(ctx, device_records, stride, 0, n, counts, prefix);
+        CK(cudaMemcpyAsync(ctx->h_result, prefix + n, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (device_moves && ctx->h_result[0] <= moves_cap) {
+          launch_moves(ctx, device_records, stride, n, prefix, device_moves, device_offsets);
+        } else {
+          k_prefix_to_offsets<<<grid_for(ctx, n + 1, 256, 8), 256, 0, ctx->stream>>>(prefix, n, device_offsets);
+          LAUNCHED();
+        }
       } else {
-        k_prefix_to_offsets<<<grid_for(ctx, n + 1, 256, 8), 256, 0, ctx->stream>>>(prefix, n, device_offsets);
-        LAUNCHED();
+        CK(cudaMemsetAsync(device_offsets, 0, sizeof(u32), ctx->stream));
+        ctx->h_result[0] = 0;
       }
-    } else {
-      CK(cudaMemsetAsync(device_offsets, 0, sizeof(u32), ctx->stream));
-      ctx->h_result[0] = 0;
+      timer.end_device();
+    } else { /* one kernel, one launch: the records are on the device already */
+      const ListInput in{nullptr, device_records, stride, ctx->d_bad_roots};
+      const size_t tiles = list_tiles(n);
+      timer.begin_device();
+      if (n) {
+        prepare_list_scan(ctx, tiles);
+        launch_list_chunk(ctx, in, n, 0, tiles, device_moves, device_moves ? moves_cap : 0, device_offsets);
+        CK(cudaMemcpyAsync(ctx->h_result, ctx->d_list_status + tiles - 1, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+      } else {
+        CK(cudaMemsetAsync(device_offsets, 0, sizeof(u32), ctx->stream));
+        ctx->h_result[0] = 0;
+      }
+      timer.end_device();
+      CK(cudaStreamSynchronize(ctx->stream));
+      ctx->h_result[0] &= (1ULL << 62) - 1;
     }
-    timer.end_device();
     timer.finish(timing, 0);
     *total_moves = ctx->h_result[0];
     if (timing) timing->algorithmic_bytes = 64 * n + 4 * (n + 1) + 2 * *total_moves;
@@ -1339,28 +1401,99 @@ int pabi_cuda_generate_moves_batch(pabi_cuda_ctx* ctx, const pabi_position_t* po
       return 0;
     }
     if (n >= 0xFFFFFFFFull / 256) return bad_arg(ctx, "batch too large for 32-bit CSR offsets");
-    upload_roots(ctx, positions, n);
-    Level& l0 = ctx->levels[0];
+    if (ctx->list_two_pass) {
+      upload_roots(ctx, positions, n);
+      Level& l0 = ctx->levels[0];
+      u32* d_offsets = (u32*)ensure(ctx, S_SMALL_A, (n + 1) * sizeof(u32));
+      u16* d_moves = moves_cap ? (u16*)ensure(ctx, S_SMALL_B, moves_cap * sizeof(u16)) : nullptr;
+      alloc_level(ctx, l0, n); /* counts/prefix of level 0 are the sizing arrays */
+      timer.begin_device();
+      count_and_scan(ctx, l0.rec, l0.cap, 0, n, l0.counts, l0.prefix);
+      CK(cudaMemcpyAsync(ctx->h_result, l0.prefix + n, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      const size_t total = (size_t)ctx->h_result[0];
+      if (total <= moves_cap && total) {
+        launch_moves(ctx, l0.rec, l0.cap, n, l0.prefix, d_moves, d_offsets);
+      } else {
+        k_prefix_to_offsets<<<grid_for(ctx, n + 1, 256, 8), 256, 0, ctx->stream>>>(l0.prefix, n, d_offsets);
+        LAUNCHED();
+      }
+      timer.end_device();
+      CK(cudaMemcpyAsync(offsets, d_offsets, (n + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+      if (total <= moves_cap && total)
+        CK(cudaMemcpyAsync(moves, d_moves, total * sizeof(u16), cudaMemcpyDeviceToHost, ctx->stream));
+      timer.finish(timing, 64 * n + 4 * (n + 1) + 2 * total);
+      if (total > moves_cap) {
+        ctx->error = "moves_cap too small; offsets[n] holds the required size";
+        return -2;
+      }
+      return 0;
+    }
+    /* The batch in chunks of LIST_CHUNK_TILES tiles, three streams: chunk c's positions travel to the device while the
+     * kernel works on chunk c-1 and the lists of chunk c-2 travel back.  The kernel reads the caller's 112-byte records
+     * directly and sizes its output itself (decoupled look-back across the chunks), so the host waits for nothing but the
+     * per-chunk totals it needs to address the copies back. */
+    const size_t tiles = list_tiles(n), chunks = (tiles + LIST_CHUNK_TILES - 1) / LIST_CHUNK_TILES;
+    PositionImage* staging = (PositionImage*)ensure(ctx, S_STAGING, n * sizeof(pabi_position_t));
     u32* d_offsets = (u32*)ensure(ctx, S_SMALL_A, (n + 1) * sizeof(u32));
     u16* d_moves = moves_cap ? (u16*)ensure(ctx, S_SMALL_B, moves_cap * sizeof(u16)) : nullptr;
-    alloc_level(ctx, l0, n); /* counts/prefix of level 0 are the sizing arrays */
-    timer.begin_device();
-    count_and_scan(ctx, l0.rec, l0.cap, 0, n, l0.counts, l0.prefix);
-    CK(cudaMemcpyAsync(ctx->h_result, l0.prefix + n, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    const size_t total = (size_t)ctx->h_result[0];
-    if (total <= moves_cap && total) {
-      launch_moves(ctx, l0.rec, l0.cap, n, l0.prefix, d_moves, d_offsets);
-    } else {
-      k_prefix_to_offsets<<<grid_for(ctx, n + 1, 256, 8), 256, 0, ctx->stream>>>(l0.prefix, n, d_offsets);
-      LAUNCHED();
+    prepare_list_scan(ctx, tiles);
+    while (ctx->list_events.size() < 4 * chunks + 1) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      ctx->list_events.push_back(e);
     }
+    if (ctx->list_totals_cap < chunks) {
+      if (ctx->h_list_totals) CK(cudaFreeHost(ctx->h_list_totals));
+      ctx->h_list_totals = nullptr;
+      CK(cudaMallocHost(&ctx->h_list_totals, (chunks + 64) * sizeof(u64)));
+      ctx->list_totals_cap = chunks + 64;
+    }
+    const ListInput in{staging, nullptr, 0, ctx->d_bad_roots};
+    cudaEvent_t ready = ctx->list_events[4 * chunks]; /* the scan words are zeroed, the scratch of an earlier call is free */
+    CK(cudaMemsetAsync(ctx->d_bad_roots, 0, sizeof(u32), ctx->stream));
+    CK(cudaEventRecord(ready, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_in, ready, 0));
+    timer.begin_device();
+    for (size_t c = 0; c < chunks; c++) {
+      const size_t t0 = c * LIST_CHUNK_TILES, t1 = std::min(tiles, t0 + LIST_CHUNK_TILES);
+      const size_t p0 = t0 * LIST_TILE, p1 = std::min(n, t1 * LIST_TILE);
+      cudaEvent_t arrived = ctx->list_events[4 * c], started = ctx->list_events[4 * c + 1], finished = ctx->list_events[4 * c + 2];
+      CK(cudaMemcpyAsync(staging + p0, positions + p0, (p1 - p0) * sizeof(pabi_position_t), cudaMemcpyHostToDevice, ctx->copy_in));
+      CK(cudaEventRecord(arrived, ctx->copy_in));
+      CK(cudaStreamWaitEvent(ctx->stream, arrived, 0));
+      CK(cudaEventRecord(started, ctx->stream));
+      launch_list_chunk(ctx, in, n, t0, t1, d_moves, moves_cap, d_offsets);
+      CK(cudaEventRecord(finished, ctx->stream));
+      CK(cudaMemcpyAsync(ctx->h_list_totals + c, ctx->d_list_status + t1 - 1, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaEventRecord(ctx->list_events[4 * c + 3], ctx->stream));
+    }
+    CK(cudaMemcpyAsync(ctx->h_bad_roots, ctx->d_bad_roots, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream)); /* read in CallTimer::finish */
     timer.end_device();
-    CK(cudaMemcpyAsync(offsets, d_offsets, (n + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-    if (total <= moves_cap && total)
-      CK(cudaMemcpyAsync(moves, d_moves, total * sizeof(u16), cudaMemcpyDeviceToHost, ctx->stream));
-    timer.finish(timing, 64 * n + 4 * (n + 1) + 2 * total);
-    if (total > moves_cap) {
+    size_t done_moves = 0;
+    bool fits = true;
+    for (size_t c = 0; c < chunks; c++) { /* the lists of a chunk go back as soon as its total is known */
+      const size_t t0 = c * LIST_CHUNK_TILES, t1 = std::min(tiles, t0 + LIST_CHUNK_TILES);
+      const size_t p0 = t0 * LIST_TILE, p1 = std::min(n, t1 * LIST_TILE);
+      CK(cudaEventSynchronize(ctx->list_events[4 * c + 3]));
+      const size_t upto = (size_t)(ctx->h_list_totals[c] & ((1ULL << 62) - 1));
+      CK(cudaMemcpyAsync(offsets + p0, d_offsets + p0, (p1 - p0 + (p1 == n ? 1 : 0)) * sizeof(u32), cudaMemcpyDeviceToHost, ctx->copy_out));
+      fits = fits && upto <= moves_cap;
+      if (fits && upto > done_moves)
+        CK(cudaMemcpyAsync(moves + done_moves, d_moves + done_moves, (upto - done_moves) * sizeof(u16), cudaMemcpyDeviceToHost, ctx->copy_out));
+      done_moves = upto;
+    }
+    CK(cudaStreamSynchronize(ctx->copy_out));
+    timer.finish(timing, 112 * n + 4 * (n + 1) + 2 * done_moves);
+    if (timing) { /* device time = the kernels alone: the stream also waited for the copies in */
+      timing->device_ms = 0;
+      for (size_t c = 0; c < chunks; c++) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->list_events[4 * c + 1], ctx->list_events[4 * c + 2]));
+        timing->device_ms += ms;
+      }
+    }
+    if (!fits) {
       ctx->error = "moves_cap too small; offsets[n] holds the required size";
       return -2;
     }

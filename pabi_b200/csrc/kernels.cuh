@@ -787,6 +787,169 @@ k_moves_warp(DeviceTables dt, const u64* __restrict__ rec, size_t stride, size_t
   }
 }
 
+/* ---- K3 fused: ordered move lists in ONE kernel ------------------------------------------------
+ * generate_moves once per position, sizes scanned inside the kernel: no separate k_count pass, no k_scan_*
+ * launches, no host round trip for the total, and the positions are read once -- straight from the caller's
+ * 112-byte images (no k_pack) or from SoA records.  Everything is warp-synchronous (no block barrier: unrelated
+ * positions take very different times to generate, see k_moves_warp):
+ *   tile = the 32 positions of one warp pass, handed out by a ticket counter
+ *   1  every lane generates its position's moves (reference order) into its column of the warp's
+ *      staging area, at most LIST_LANE_CAP of them; the generator's return value is the count
+ *   2  warp scan of the counts: where each list starts inside the tile
+ *   3  decoupled look-back over the tiles before it, 32 status words at a time (aggregate / inclusive
+ *      prefix), gives the tile's place in the whole batch; tiles of earlier launches of the same batch are
+ *      complete, so a batch may be cut into chunks whose copies overlap the kernels
+ *   4  offsets are written; the warp copies its staged lists to the CSR array with coalesced stores (the
+ *      source lane of an output slot is found by a shuffle binary search over the lanes' offsets).  A warp
+ *      holding a position with more than LIST_LANE_CAP moves regenerates into a sliding window instead.
+ * Moves beyond moves_cap are not written; offsets[n] always holds the total, so the caller can retry. */
+constexpr int LIST_THREADS = 1024;
+constexpr int LIST_LANE_CAP = 64; /* staged moves per position; the playout positions average 27.6, the record is 218 */
+
+struct ListShared {
+  SharedTables tables;
+  u16 stage[LIST_THREADS / 32][32 * LIST_LANE_CAP]; /* [warp][k * 32 + lane]: lanes write neighbouring half-words */
+};
+
+struct ListScan {
+  unsigned long long* status; /* one word per tile of the batch: bits 62-63 state (1 aggregate, 2 inclusive prefix), bits 0-61 moves */
+  unsigned long long* ticket; /* zeroed before every launch */
+  size_t tile_begin, tile_end; /* this launch covers these tiles of the batch */
+};
+
+struct ListInput {
+  const PositionImage* aos; /* the caller's records, or null: */
+  const u64* rec;           /* SoA records */
+  size_t stride;
+  u32* bad;                 /* aos: records that are not positions (see k_pack) */
+};
+
+__device__ __forceinline__ Pos list_position(const ListInput& in, size_t i) {
+  if (!in.aos) return load_pos(in.rec, in.stride, i);
+  const PositionImage& q = in.aos[i];
+  Pos p;
+  p.white = q.white[0] | q.white[1] | q.white[2] | q.white[3] | q.white[4] | q.white[5];
+  p.kings = q.white[0] | q.black[0];
+  p.queens = q.white[1] | q.black[1];
+  p.rooks = q.white[2] | q.black[2];
+  p.bishops = q.white[3] | q.black[3];
+  p.knights = q.white[4] | q.black[4];
+  p.pawns = q.white[5] | q.black[5];
+  p.meta = make_meta(q.castling & 15, q.ep > 63 ? NO_SQUARE : q.ep, q.stm & 1, q.halfmove, q.fullmove);
+  if (popc(q.white[0]) != 1 || popc(q.black[0]) != 1 || (p.pawns & (RANK_1 | RANK_8))) {
+    atomicAdd(in.bad, 1u);
+    p.white = p.kings = bit(0), p.kings |= bit(63);
+    p.pawns = p.knights = p.bishops = p.rooks = p.queens = 0;
+    p.meta = make_meta(0, NO_SQUARE, 0, 0, 1);
+  }
+  return p;
+}
+
+__global__ void __launch_bounds__(LIST_THREADS, 1)
+k_moves_fused(DeviceTables dt, ListInput in, size_t n, ListScan scan, u16* __restrict__ moves, size_t moves_cap, u32* __restrict__ offsets) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  ListShared& sh = *reinterpret_cast<ListShared*>(smem);
+  if ((size_t)blockIdx.x * (LIST_THREADS / 32) >= scan.tile_end - scan.tile_begin) return;
+  stage_tables(&sh.tables, dt.image);
+  const Tables tb{&sh.tables, dt.g};
+  const int lane = threadIdx.x & 31;
+  u16* stage = sh.stage[threadIdx.x >> 5];
+  constexpr unsigned long long VALUE = (1ULL << 62) - 1;
+  for (;;) {
+    unsigned long long ticket = 0;
+    if (lane == 0) ticket = atomicAdd(scan.ticket, 1ULL);
+    const size_t tile = scan.tile_begin + (size_t)__shfl_sync(0xFFFFFFFFu, ticket, 0);
+    if (tile >= scan.tile_end) break;
+    const size_t i = tile * 32 + lane;
+    const bool valid = i < n;
+    Pos p;
+    u32 cnt = 0;
+    if (valid) { /* 1: the moves, staged */
+      p = list_position(in, i);
+      u32 k = 0;
+      cnt = generate_moves(p, tb, [&](int from, int to, int promo, int) {
+        if (k < (u32)LIST_LANE_CAP) stage[k * 32 + lane] = pack_move(from, to, promo);
+        ++k;
+      });
+    }
+    /* 2: where every list starts inside the tile */
+    u32 inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    const u32 off = inc - cnt, total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    const bool fat = __any_sync(0xFFFFFFFFu, cnt > (u32)LIST_LANE_CAP);
+    /* 3: the tile's place in the batch */
+    unsigned long long base = 0;
+    if (tile > 0) {
+      if (lane == 0) {
+        __threadfence();
+        atomicExch(scan.status + tile, (1ULL << 62) | total);
+      }
+      for (long long look = (long long)tile - 1;; look -= 32) { /* 32 predecessors per step, the nearest in lane 0 */
+        const long long t = look - lane;
+        unsigned long long s = 2ULL << 62; /* before the first tile: an inclusive prefix of zero */
+        if (t >= 0) do s = atomicAdd(scan.status + t, 0ULL); while ((s >> 62) == 0);
+        const unsigned inclusive = __ballot_sync(0xFFFFFFFFu, (s >> 62) == 2);
+        const int stop = inclusive ? __ffs((int)inclusive) - 1 : 31; /* the nearest predecessor that knows its whole prefix */
+        unsigned long long v = lane <= stop ? s & VALUE : 0;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        base += v;
+        if (inclusive) break;
+      }
+    }
+    if (lane == 0) {
+      __threadfence();
+      atomicExch(scan.status + tile, (2ULL << 62) | (base + total));
+    }
+    if (valid) {
+      offsets[i] = (u32)(base + off);
+      if (i + 1 == n) offsets[n] = (u32)(base + off + cnt);
+    }
+    /* 4: the lists */
+    if (base + total <= moves_cap) {
+      if (!fat) {
+#ifdef PABI_LIST_SCATTER /* measured alternative: every lane stores its own list, 2-byte stores 32 sectors wide */
+        for (u32 k = 0; __any_sync(0xFFFFFFFFu, k < cnt); k++)
+          if (k < cnt) moves[base + off + k] = stage[k * 32 + lane];
+#else
+        for (u32 c0 = 0; c0 < total; c0 += 32) { /* whole warps take every trip: the shuffles need all lanes */
+          const u32 c = c0 + lane;
+          int owner = 0; /* the last lane whose list starts at or before slot c */
+#pragma unroll
+          for (int step = 16; step; step >>= 1) {
+            const int probe = owner + step;
+            const u32 start = __shfl_sync(0xFFFFFFFFu, off, probe & 31);
+            if (probe < 32 && start <= c) owner = probe;
+          }
+          const u32 first = __shfl_sync(0xFFFFFFFFu, off, owner);
+          if (c < total) moves[base + c] = stage[(c - first) * 32 + owner];
+        }
+#endif
+      } else { /* a list longer than a staging column: sliding windows over the warp's lists, regenerated */
+        constexpr u32 WINDOW = 32 * LIST_LANE_CAP;
+        for (u32 w = 0; w < total; w += WINDOW) {
+          __syncwarp();
+          if (cnt && off < w + WINDOW && off + cnt > w) {
+            u32 j = off;
+            generate_moves(p, tb, [&](int from, int to, int promo, int) {
+              const u32 slot = j++ - w; /* wraps to a huge value below the window */
+              if (slot < WINDOW) stage[slot] = pack_move(from, to, promo);
+            });
+          }
+          __syncwarp();
+          const u32 end = min(total - w, WINDOW);
+          for (u32 c = lane; c < end; c += 32) moves[base + w + c] = stage[c];
+        }
+      }
+    }
+    __syncwarp(); /* the staging area is reused by the next tile */
+  }
+}
+
 /* ---- transposition merging (perft "with hashing", made exact) -------------------------------
  * Records of one ply that are the same position (placement, side to move, castling rights, en
  * passant square; the clocks do not influence perft) are merged into one record whose multiplicity
