@@ -243,8 +243,9 @@ int pabi_cuda_games_play_random(pabi_cuda_games* games, const uint64_t* seeds /*
                                 uint8_t* results /* [n] */, uint32_t* plies /* [n] */, pabi_timing_t* timing);
 
 /* ---- device-resident variants (inputs/outputs already in HBM) ------------- */
-/* Positions in the 64-byte SoA record: word w of record i at
- * records[w * stride + i].  Used by bench.py to time the kernels without copies. */
+/* Positions as 64-byte device records: the eight words of pabi_position_pack64 in
+ * pairs, pair k (words 2k, 2k+1) of record i at records[(k * stride + i) * 2]; `records` holds 8 * stride
+ * words and must be 16-byte aligned.  Used by bench.py to time the kernels without copies. */
 int pabi_cuda_pack_records(pabi_cuda_ctx* ctx, const pabi_position_t* positions, size_t n,
                            uint64_t* device_records, size_t stride);
 int pabi_cuda_generate_moves_device(pabi_cuda_ctx* ctx, const uint64_t* device_records, size_t stride, size_t n,

@@ -74,7 +74,7 @@ struct PositionImage { /* == pabi_position_t (include/pabi_cuda.h) */
 };
 static_assert(sizeof(PositionImage) == 112, "pabi_position_t image");
 
-/* SoA view of a frontier: word w of record i at rec[w * stride + i]. */
+/* View of a frontier: records in word pairs, pair k of record i at rec[(k * stride + i) * 2] (load_pos / store_pos). */
 struct Frontier {
   u64* rec;
   u32* roots; /* root index of each record (perft_batch), may be null when single-root */
@@ -1170,8 +1170,10 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
           const size_t next_first = (size_t)sh.next_tile * PARENTS + tid;
           if (next_first < n) {
 #pragma unroll
-            for (int w = 0; w < POS_WORDS; w++)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(in.rec + (size_t)w * in.stride + first + next_first));
+            for (int w = 0; w < POS_WORDS / 2; w++) { /* 16 records of a pair array are two 128-byte lines */
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(in.rec + ((size_t)w * in.stride + first + next_first) * 2));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(in.rec + ((size_t)w * in.stride + first + next_first) * 2 + 16));
+            }
           }
         }
         inert_children += inert_moves;

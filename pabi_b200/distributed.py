@@ -42,6 +42,19 @@ def all_reduce_max(values, device: Optional[torch.device] = None):
     return t.tolist()
 
 
+def shard_of(record_words, shard_count: int) -> int:
+    """The shard a subtree belongs to under `pabi_cuda_perft_shard`: a hash of its root's 64-byte record (the eight words
+    of `Position.pack64()`) modulo the shard count -- `shard_hash` of pabi_b200/csrc/kernels.cuh, restated here so that the
+    contract is checkable on the host.  A property of the position alone, whatever the order of the frontier."""
+    mask = 0xFFFFFFFFFFFFFFFF
+    h = 0x9E3779B97F4A7C15
+    for w in record_words:
+        h = ((h ^ int(w)) * 0xBF58476D1CE4E5B9) & mask
+        h ^= h >> 29
+    h = (h * 0x94D049BB133111EB) & mask
+    return (h ^ (h >> 32)) % shard_count
+
+
 def shard_ranges(n_items: int, rank: int, world_size: int) -> range:
     """Interleaved assignment used for books / position batches: items rank, rank + world, ..."""
     return range(rank, n_items, world_size)

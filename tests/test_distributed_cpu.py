@@ -33,7 +33,11 @@ class OracleEngine:
                     oracle.make_move(c, m)
                     nxt.append(c)
             frontier = nxt
-        return sum(oracle.perft(p, depth - plies) for p in frontier[shard_index::shard_count])
+        # a subtree's shard is a hash of its root record (pabi_b200.distributed.shard_of), not its place in the frontier
+        import pabi_b200 as pb
+        from pabi_b200 import distributed as D
+        mine = [p for p in frontier if D.shard_of(pb.Position.from_fen(oracle.to_fen(p)).pack64(), shard_count) == shard_index]
+        return sum(oracle.perft(p, depth - plies) for p in mine)
 
     def perft_batch(self, positions, depth):
         return np.array([oracle.perft(oracle.Position.from_buffer_copy(positions[i].tobytes()), depth)

@@ -613,3 +613,16 @@ def test_speculative_plies_fall_back_to_the_exact_path_when_a_buffer_overflows(p
     assert sum(tiny.perft_shard(dense, 4, 2, i, 3) for i in range(3)) == 169711264
     assert tiny.perft(pb.Position.starting(), 6) == 119060324
     tiny.close()
+
+
+def test_shard_assignment_is_the_documented_hash_of_the_record(pb, engine, playout_positions):
+    """pabi_cuda_perft_shard keeps the subtrees whose root record hashes to its shard (pabi_b200.distributed.shard_of restates
+    the hash on the host).  With split_ply 0 the root itself is the subtree: exactly one shard returns its count."""
+    from pabi_b200 import distributed as D
+    for i in range(0, 3000, 97):
+        p = pb.Position.from_record(playout_positions[i])
+        whole = engine.perft(p, 2)
+        for count in (2, 8):
+            owner = D.shard_of(p.pack64(), count)
+            got = [engine.perft_shard(p, 2, 0, s, count) for s in range(count)]
+            assert got == [whole if s == owner else 0 for s in range(count)], (i, count)
