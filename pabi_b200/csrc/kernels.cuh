@@ -1046,7 +1046,7 @@ struct TileConfig {
 
 template <class CFG>
 struct TileGroupShared {
-  u64 parents[POS_WORDS][CFG::PARENTS];
+  ulonglong2 parents[POS_WORDS / 2][CFG::PARENTS]; /* word pairs: a parent is read with four 128-bit loads */
   u32 pool[CFG::POOL];
   u32 parent_nodes[CFG::PARENTS]; /* K2, multi-root: nodes below each parent */
   u64 warp_sums[CFG::GROUP_THREADS / 32 + 1];
@@ -1065,9 +1065,15 @@ struct TileShared {
 template <class CFG>
 __device__ __forceinline__ Pos tile_parent(const TileGroupShared<CFG>& sh, int k) {
   Pos q;
-  q.white = sh.parents[0][k], q.pawns = sh.parents[1][k], q.knights = sh.parents[2][k], q.bishops = sh.parents[3][k];
-  q.rooks = sh.parents[4][k], q.queens = sh.parents[5][k], q.kings = sh.parents[6][k], q.meta = sh.parents[7][k];
+  const ulonglong2 a = sh.parents[0][k], b = sh.parents[1][k], c = sh.parents[2][k], d = sh.parents[3][k];
+  q.white = a.x, q.pawns = a.y, q.knights = b.x, q.bishops = b.y, q.rooks = c.x, q.queens = c.y, q.kings = d.x, q.meta = d.y;
   return q;
+}
+
+template <class CFG>
+__device__ __forceinline__ void put_tile_parent(TileGroupShared<CFG>& sh, int k, const Pos& p) {
+  sh.parents[0][k] = make_ulonglong2(p.white, p.pawns), sh.parents[1][k] = make_ulonglong2(p.knights, p.bishops);
+  sh.parents[2][k] = make_ulonglong2(p.rooks, p.queens), sh.parents[3][k] = make_ulonglong2(p.kings, p.meta);
 }
 
 enum TileMode {
@@ -1152,9 +1158,7 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
           if (meta_stm(p.meta) == 0) p = mirror(p);
           const TContext ctx = t_context(p, tb);
           p.meta = (with_king_squares(p) & ~(0xFFFFULL << META_BASE)) | ((u64)ctx.base << META_BASE);
-          sh.parents[0][tid] = p.white, sh.parents[1][tid] = p.pawns, sh.parents[2][tid] = p.knights;
-          sh.parents[3][tid] = p.bishops, sh.parents[4][tid] = p.rooks, sh.parents[5][tid] = p.queens;
-          sh.parents[6][tid] = p.kings, sh.parents[7][tid] = p.meta;
+          put_tile_parent(sh, tid, p);
           DirectEmitter emit{sh.pool, &sh.cursor, &sh.overflow, (u32)POOL, (u32)tid << 16, ctx.zone};
           enumerate_split(p, tb, ctx.reach, ctx.guard, emit);
           inert_moves = emit.inert;
@@ -1212,9 +1216,7 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
     u64 out_base = 0; /* global index of this tile's first child / move */
     if (valid) {
       const Pos p = load_pos(in.rec, in.stride, first + i);
-      sh.parents[0][tid] = p.white, sh.parents[1][tid] = p.pawns, sh.parents[2][tid] = p.knights;
-      sh.parents[3][tid] = p.bishops, sh.parents[4][tid] = p.rooks, sh.parents[5][tid] = p.queens;
-      sh.parents[6][tid] = p.kings, sh.parents[7][tid] = p.meta;
+      put_tile_parent(sh, tid, p);
       if (ATOMIC) cnt = count_moves(p, tb);
     }
     if (ATOMIC) {
