@@ -804,6 +804,9 @@ k_moves_warp(DeviceTables dt, const u64* __restrict__ rec, size_t stride, size_t
  *      holding a position with more than LIST_LANE_CAP moves regenerates into a sliding window instead.
  * Moves beyond moves_cap are not written; offsets[n] always holds the total, so the caller can retry. */
 constexpr int LIST_THREADS = 1024;
+#ifndef PABI_LIST_SLEEP_NS
+#define PABI_LIST_SLEEP_NS 200
+#endif
 constexpr int LIST_LANE_CAP = 64; /* staged moves per position; the playout positions average 27.6, the record is 218 */
 
 struct ListShared {
@@ -891,7 +894,8 @@ k_moves_fused(DeviceTables dt, ListInput in, size_t n, ListScan scan, u16* __res
       for (long long look = (long long)tile - 1;; look -= 32) { /* 32 predecessors per step, the nearest in lane 0 */
         const long long t = look - lane;
         unsigned long long s = 2ULL << 62; /* before the first tile: an inclusive prefix of zero */
-        if (t >= 0) do s = atomicAdd(scan.status + t, 0ULL); while ((s >> 62) == 0);
+        if (t >= 0) /* a predecessor that is still generating: sleep instead of spinning, the issue slots belong to the generators */
+          while (((s = atomicAdd(scan.status + t, 0ULL)) >> 62) == 0) __nanosleep(PABI_LIST_SLEEP_NS);
         const unsigned inclusive = __ballot_sync(0xFFFFFFFFu, (s >> 62) == 2);
         const int stop = inclusive ? __ffs((int)inclusive) - 1 : 31; /* the nearest predecessor that knows its whole prefix */
         unsigned long long v = lane <= stop ? s & VALUE : 0;
