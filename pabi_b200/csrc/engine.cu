@@ -86,6 +86,9 @@ struct pabi_cuda_ctx {
   unsigned long long* h_fast = nullptr; /* pinned */
   int fast_used = 0;                    /* counters handed out in this call */
   std::vector<int> fast_interior, fast_leaf; /* counters whose frontier was expanded / was the input of K2 (statistics) */
+  struct FastEdge { size_t parent_n; int parent_slot, child_slot; }; /* a speculative ply: parent (exact size or counter) -> children's counter */
+  std::vector<FastEdge> fast_edges;
+  double branching = 0; /* children per position of the last speculative ply whose two sizes are known (0: none yet) */
   bool exact_only = false;              /* this call walks on the exact path (a speculative walk overflowed, or PABI_EXACT_LEVELS=1) */
   bool force_exact = false;
   /* move lists (K3 fused): a second and a third stream so that the copies of a batch overlap its kernels */
@@ -457,10 +460,18 @@ unsigned long long* fast_counter(pabi_cuda_ctx* ctx) { /* a zeroed device counte
 size_t exact_size(pabi_cuda_ctx* ctx, const Sized& s) {
   if (!s.n_dev) return s.n;
   const size_t slot = (size_t)(s.n_dev - ctx->d_fast);
-  CK(cudaMemcpyAsync(ctx->h_fast + slot, s.n_dev, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_fast, ctx->d_fast, ctx->fast_used * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream)); /* every counter so far */
   CK(cudaMemcpyAsync(ctx->h_fast + FAST_SLOTS - 1, ctx->d_fast + FAST_SLOTS - 1, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (ctx->h_fast[FAST_SLOTS - 1]) throw Redo{};
+  for (auto e = ctx->fast_edges.rbegin(); e != ctx->fast_edges.rend(); ++e) { /* the measured branching of the deepest finished ply */
+    const double parents = e->parent_slot >= 0 ? (double)ctx->h_fast[e->parent_slot] : (double)e->parent_n;
+    const double children = (double)ctx->h_fast[e->child_slot];
+    if (parents > 0 && children > 0) {
+      ctx->branching = children / parents;
+      break;
+    }
+  }
   return (size_t)ctx->h_fast[slot];
 }
 
@@ -594,17 +605,29 @@ void descend(pabi_cuda_ctx* ctx, int lv, Sized s, int remaining, Accounting acc,
     return;
   }
   unsigned long long* n_children = nullptr;
-  const bool speculate = !ctx->exact_only && acc != WEIGHTED && lv + 1 < MAX_LEVELS &&
-                         s.n * BRANCH_ESTIMATE * BRANCH_MARGIN <= ctx->capacity && (n_children = fast_counter(ctx)) != nullptr;
+  const bool may_speculate = !ctx->exact_only && acc != WEIGHTED && lv + 1 < MAX_LEVELS;
+  bool speculate = may_speculate && s.n * BRANCH_ESTIMATE * BRANCH_MARGIN <= ctx->capacity && (n_children = fast_counter(ctx)) != nullptr;
   if (!speculate) {
-    descend_exact(ctx, lv, exact_size(ctx, s), remaining, acc);
-    return;
+    /* the estimate is too large for the buffer: fetch the exact size.  If the branching of the plies above is known by
+     * then (it is whenever they were speculative), one more ply may still go without its sizing pass: this size x the
+     * measured branching x 1.6 must fit (sides alternate, so consecutive plies differ; a miss costs a redo, never a count) */
+    const size_t n = exact_size(ctx, s);
+    if (n == 0) return;
+    s = Sized{n, nullptr};
+    speculate = may_speculate && s.n_dev == nullptr && ctx->branching > 0 &&
+                (double)n * ctx->branching * 1.6 <= (double)ctx->capacity && (n_children = fast_counter(ctx)) != nullptr;
+    if (!speculate) {
+      descend_exact(ctx, lv, n, remaining, acc);
+      return;
+    }
   }
   alloc_level(ctx, ctx->levels[lv + 1], ctx->capacity);
   note_size(ctx, s, false);
   launch_expand_atomic(ctx, acc, frontier_of(ctx->levels[lv]), s.n, s.n_dev, frontier_of(ctx->levels[lv + 1]), ctx->levels[lv + 1].cap,
                        n_children);
-  descend(ctx, lv + 1, Sized{s.n * BRANCH_ESTIMATE, n_children}, remaining - 1, acc, true);
+  ctx->fast_edges.push_back({s.n, s.n_dev ? (int)(s.n_dev - ctx->d_fast) : -1, (int)(n_children - ctx->d_fast)});
+  const size_t estimate = ctx->branching > 0 && !s.n_dev ? (size_t)((double)s.n * ctx->branching) : s.n * BRANCH_ESTIMATE;
+  descend(ctx, lv + 1, Sized{estimate, n_children}, remaining - 1, acc, true);
 }
 
 struct CallTimer {
@@ -694,7 +717,7 @@ int perft_impl(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, int d
     ctx->shard_level = shard_count > 1 ? (int)std::min<uint32_t>(split_ply, (uint32_t)depth - 1) : -1;
     for (int attempt = 0;; attempt++) {
       ctx->exact_only = ctx->force_exact || attempt > 0;
-      ctx->fast_used = 0, ctx->fast_interior.clear(), ctx->fast_leaf.clear();
+      ctx->fast_used = 0, ctx->fast_interior.clear(), ctx->fast_leaf.clear(), ctx->fast_edges.clear(), ctx->branching = 0;
       ctx->interior = 0, ctx->leaf_parents = 0, ctx->leaf_launches = 0;
       CK(cudaMemsetAsync(ctx->d_nodes, 0, n_out * sizeof(unsigned long long), ctx->stream));
       CK(cudaMemsetAsync(ctx->d_visited, 0, sizeof(unsigned long long), ctx->stream));
