@@ -469,6 +469,24 @@ def test_one_million_move_lists_bit_exact(engine):
     assert np.array_equal(offsets, want_offsets)
     assert np.array_equal(moves, want_moves)
     assert len(moves) > 20_000_000
+    # the same lists against the independent brute-force generator (sorted sets, in_check too), as the reference
+    # does against shakmaty (tests/chess.rs:555-578)
+    import brute
+    checks = engine.in_check_batch(positions)
+    bad, first, total = brute.compare_batch(positions, offsets, moves, checks)
+    assert bad == 0 and total == len(moves), oracle.to_fen(oracle.Position.from_buffer_copy(positions[first].tobytes()))
+    # and the two-pass path of round 1 (count, scan, emit) is still exact
+    two_pass = np.ascontiguousarray(positions[:200_000])
+    import os
+    os.environ["PABI_LIST_TWO_PASS"] = "1"
+    try:
+        import pabi_b200
+        e2 = pabi_b200.Engine(0)
+        o2, m2 = e2.generate_moves_batch(two_pass)
+        e2.close()
+    finally:
+        del os.environ["PABI_LIST_TWO_PASS"]
+    assert np.array_equal(o2, want_offsets[:200_001]) and np.array_equal(m2, want_moves[:want_offsets[200_000]])
 
 
 def test_startpos_perft_8(pb, engine):
