@@ -916,10 +916,6 @@ k_moves_fused(DeviceTables dt, ListInput in, size_t n, ListScan scan, u16* __res
     /* 4: the lists */
     if (base + total <= moves_cap) {
       if (!fat) {
-#ifdef PABI_LIST_SCATTER /* measured alternative: every lane stores its own list, 2-byte stores 32 sectors wide */
-        for (u32 k = 0; __any_sync(0xFFFFFFFFu, k < cnt); k++)
-          if (k < cnt) moves[base + off + k] = stage[k * 32 + lane];
-#else
         for (u32 c0 = 0; c0 < total; c0 += 32) { /* whole warps take every trip: the shuffles need all lanes */
           const u32 c = c0 + lane;
           int owner = 0; /* the last lane whose list starts at or before slot c */
@@ -932,7 +928,6 @@ k_moves_fused(DeviceTables dt, ListInput in, size_t n, ListScan scan, u16* __res
           const u32 first = __shfl_sync(0xFFFFFFFFu, off, owner);
           if (c < total) moves[base + c] = stage[(c - first) * 32 + owner];
         }
-#endif
       } else { /* a list longer than a staging column: sliding windows over the warp's lists, regenerated */
         constexpr u32 WINDOW = 32 * LIST_LANE_CAP;
         for (u32 w = 0; w < total; w += WINDOW) {
