@@ -91,6 +91,7 @@ struct pabi_cuda_ctx {
   double branching = 0; /* children per position of the last speculative ply whose two sizes are known (0: none yet) */
   bool exact_only = false;              /* this call walks on the exact path (a speculative walk overflowed, or PABI_EXACT_LEVELS=1) */
   bool force_exact = false;
+  bool no_virtual = false;              /* PABI_NO_VIRTUAL_PLY=1: the ply above K2 is always materialised (comparison runs) */
   /* move lists (K3 fused): a second and a third stream so that the copies of a batch overlap its kernels */
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   std::vector<cudaEvent_t> list_events; /* per chunk: positions on the device, kernel started, kernel finished */
@@ -260,7 +261,8 @@ void launch_leaf_acc(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n, 
 
 /* K2: the last two plies below the n records of `in`.  With n_dev the true size is *n_dev (on the device) and n is the
  * estimate the launch geometry is chosen for. */
-void launch_leaf(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n, const unsigned long long* n_dev = nullptr) {
+void launch_leaf(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n, const unsigned long long* n_dev = nullptr,
+                 const unsigned long long* virt = nullptr) {
   while (ctx->leaf_events.size() < 2 * (ctx->leaf_launches + 1)) {
     cudaEvent_t e;
     CK(cudaEventCreate(&e));
@@ -269,7 +271,7 @@ void launch_leaf(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n, cons
   CK(cudaEventRecord(ctx->leaf_events[2 * ctx->leaf_launches], ctx->stream));
   CK(cudaMemsetAsync(ctx->d_visited + 1, 0, sizeof(unsigned long long), ctx->stream)); /* the tile ticket counter */
   TileOut out{Frontier{nullptr, nullptr, 0, nullptr}, nullptr, nullptr, ctx->d_nodes, ctx->d_visited, ctx->d_visited + 1};
-  out.n_in = n_dev;
+  out.n_in = n_dev, out.virt = virt;
   /* below one default tile per thread group of the grid the frontier is cut into shorter tiles (measured: 197 281
    * parents are still faster with 256-parent tiles, 97 862 with 64-parent ones) */
   const size_t groups = (size_t)ctx->sm_count * TileDefault::GROUPS;
@@ -305,6 +307,23 @@ template <class CFG>
 void launch_expand_atomic_acc(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n, const TileOut& out) {
   if (acc == PER_ROOT) launch_tile_cfg<TILE_EXPAND_ATOMIC, PER_ROOT, CFG>(ctx, in, 0, n, nullptr, out);
   else launch_tile_cfg<TILE_EXPAND_ATOMIC, SINGLE_ROOT, CFG>(ctx, in, 0, n, nullptr, out);
+}
+
+/* The same for a virtual frontier (TILE_EXPAND_VIRTUAL): the children of records [first, first + n) of `in` as 8-byte entries */
+template <class CFG>
+void launch_expand_virtual_acc(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t first, size_t n, const TileOut& out) {
+  if (acc == PER_ROOT) launch_tile_cfg<TILE_EXPAND_VIRTUAL, PER_ROOT, CFG>(ctx, in, first, n, nullptr, out);
+  else launch_tile_cfg<TILE_EXPAND_VIRTUAL, SINGLE_ROOT, CFG>(ctx, in, first, n, nullptr, out);
+}
+
+void launch_expand_virtual(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t first, size_t n, const unsigned long long* n_dev,
+                           unsigned long long* entries, size_t entries_cap, unsigned long long* n_out) {
+  TileOut out{Frontier{nullptr, nullptr, 0, nullptr}, nullptr, nullptr, nullptr, nullptr, nullptr};
+  out.n_in = n_dev, out.n_out = n_out, out.overflow = ctx->d_fast + FAST_SLOTS - 1, out.out_cap = entries_cap, out.virt_out = entries;
+  const size_t groups = (size_t)ctx->sm_count * TileDefault::GROUPS;
+  if (n < groups * TileSmall::PARENTS) launch_expand_virtual_acc<TileTiny>(ctx, acc, in, first, n, out);
+  else if (n < groups * TileDefault::PARENTS) launch_expand_virtual_acc<TileSmall>(ctx, acc, in, first, n, out);
+  else launch_expand_virtual_acc<TileDefault>(ctx, acc, in, first, n, out);
 }
 
 void launch_expand_atomic(pabi_cuda_ctx* ctx, Accounting acc, Frontier in, size_t n, const unsigned long long* n_dev, Frontier children,
@@ -579,6 +598,45 @@ void descend_exact(pabi_cuda_ctx* ctx, int lv, size_t n, int remaining, Accounti
   }
 }
 
+/* Three plies left: the ply below level lv is not materialised.  K1 writes every child of the level as an 8-byte
+ * (parent index, kind, move) entry (TILE_EXPAND_VIRTUAL, into the next level's record buffer, which holds 8 entries per
+ * record slot) and K2 makes each of its parents from such an entry and the parent's record, then walks the last two plies as
+ * always.  Against the materialised ply this writes and reads 8 instead of 64 bytes per position and needs no sizing pass;
+ * the price is one make_move per K2 parent inside the ALU-bound K2.  The level's records go in chunks sized from the
+ * measured (or assumed) branching; a chunk whose entries overflow the buffer after all raises the flag (-> exact redo). */
+bool virtual_ply(pabi_cuda_ctx* ctx, int lv, Sized s, Accounting acc) {
+  if (ctx->capacity >= (size_t(1) << 32)) return false; /* an entry holds a 32-bit record index */
+  alloc_level(ctx, ctx->levels[lv + 1], ctx->capacity);
+  const size_t entries_cap = ctx->levels[lv + 1].cap * POS_WORDS;
+  unsigned long long* entries = (unsigned long long*)ctx->levels[lv + 1].rec;
+  if (s.n_dev && (double)s.n * (double)(BRANCH_ESTIMATE * BRANCH_MARGIN) <= (double)entries_cap) {
+    /* a small level sized on the device: one chunk is certain to do, so the host need not learn the size */
+    unsigned long long* made = fast_counter(ctx);
+    if (!made) return false;
+    note_size(ctx, s, false);
+    launch_expand_virtual(ctx, acc, frontier_of(ctx->levels[lv]), 0, s.n, s.n_dev, entries, entries_cap, made);
+    const int slot = (int)(made - ctx->d_fast);
+    ctx->fast_interior.push_back(slot), ctx->fast_leaf.push_back(slot);
+    launch_leaf(ctx, acc, frontier_of(ctx->levels[lv]), s.n * BRANCH_ESTIMATE, made, entries);
+    return true;
+  }
+  const size_t n = exact_size(ctx, s); /* chunk boundaries are host decisions */
+  if (n == 0) return true;
+  const double per_parent = ctx->branching > 0 ? ctx->branching * 1.6 : (double)(BRANCH_ESTIMATE * BRANCH_MARGIN);
+  const size_t chunk = (size_t)std::min<double>((double)n, (double)entries_cap / per_parent);
+  if (chunk == 0 || (n + chunk - 1) / chunk > (size_t)(FAST_SLOTS - 1 - ctx->fast_used)) return false;
+  ctx->interior += n;
+  for (size_t start = 0; start < n; start += chunk) {
+    const size_t len = std::min(chunk, n - start);
+    unsigned long long* made = fast_counter(ctx);
+    launch_expand_virtual(ctx, acc, frontier_of(ctx->levels[lv]), start, len, nullptr, entries, entries_cap, made);
+    const int slot = (int)(made - ctx->d_fast);
+    ctx->fast_interior.push_back(slot), ctx->fast_leaf.push_back(slot);
+    launch_leaf(ctx, acc, frontier_of(ctx->levels[lv]), (size_t)((double)len * per_parent / 1.6), made, entries);
+  }
+  return true;
+}
+
 /* Walks `remaining` plies below the records of level `lv`, adding leaf counts to d_nodes (per root for PER_ROOT; times the
  * record's multiplicity for WEIGHTED, where every expanded chunk is passed through merge_transpositions).
  *
@@ -604,8 +662,9 @@ void descend(pabi_cuda_ctx* ctx, int lv, Sized s, int remaining, Accounting acc,
     launch_leaf(ctx, acc, frontier_of(ctx->levels[lv]), s.n, s.n_dev);
     return;
   }
-  unsigned long long* n_children = nullptr;
   const bool may_speculate = !ctx->exact_only && acc != WEIGHTED && lv + 1 < MAX_LEVELS;
+  if (remaining == 3 && may_speculate && !split_below && !ctx->no_virtual && virtual_ply(ctx, lv, s, acc)) return;
+  unsigned long long* n_children = nullptr;
   bool speculate = may_speculate && s.n * BRANCH_ESTIMATE * BRANCH_MARGIN <= ctx->capacity && (n_children = fast_counter(ctx)) != nullptr;
   if (!speculate) {
     /* the estimate is too large for the buffer: fetch the exact size.  If the branching of the plies above is known by
@@ -797,6 +856,7 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     CK(cudaMalloc(&ctx->d_fast, FAST_SLOTS * sizeof(u64)));
     CK(cudaMallocHost(&ctx->h_fast, FAST_SLOTS * sizeof(u64)));
     if (const char* v = std::getenv("PABI_EXACT_LEVELS")) ctx->force_exact = std::atoi(v) != 0; /* no speculative plies (comparison runs) */
+    if (const char* v = std::getenv("PABI_NO_VIRTUAL_PLY")) ctx->no_virtual = std::atoi(v) != 0;
     CK(cudaMalloc(&ctx->d_bad_roots, sizeof(u32)));
     CK(cudaMallocHost(&ctx->h_bad_roots, sizeof(u32)));
     *ctx->h_bad_roots = 0;
@@ -829,6 +889,7 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
       ctx->tile_variant = std::atoi(v);
       if (ctx->tile_variant != 9 && ctx->tile_variant != 8 && (ctx->tile_variant < 0 || ctx->tile_variant >= TILE_VARIANTS)) ctx->tile_variant = 0;
       if (ctx->tile_variant == 9) ctx->list_two_pass = true; /* the block-level K3 needs the scanned offsets */
+      if (ctx->tile_variant == 8) ctx->no_virtual = true;    /* the warp-synchronous K2 reads materialised parents only */
     }
   } catch (const CudaFail& f) {
     std::fprintf(stderr, "pabi_cuda_create: %s\n", ctx->error.c_str());

@@ -1079,6 +1079,9 @@ enum TileMode {
   TILE_LEAF,   /* K2: count the children, write nothing */
   TILE_EXPAND, /* K1: write the children as SoA records */
   TILE_MOVES,  /* K3: write the moves themselves (u16, CSR) */
+  TILE_EXPAND_VIRTUAL, /* as TILE_EXPAND_ATOMIC, but the children are not made: a child is written as an 8-byte entry
+                          (index of its parent record, kind of the moving piece, move), and K2 makes it itself.  The ply
+                          below the last materialised one costs 8 instead of 64 bytes per position to write and to read */
   TILE_EXPAND_ATOMIC /* K1 without a sizing pass: a tile counts its own parents, scans the counts inside the thread group and
                         reserves its children's range with ONE atomicAdd on the next level's record counter.  The children of a
                         ply land in no particular tile order (perft does not care), there is no k_count / k_scan_* launch, and the
@@ -1098,6 +1101,9 @@ struct TileOut {
   unsigned long long* overflow;     /* TILE_EXPAND_ATOMIC: set when a tile's children would not fit out_cap (the host then redoes
                                        the call on the exact, chunked path) */
   size_t out_cap;
+  /* a virtual frontier: entry = parent record index << 32 | kind << 16 | move */
+  unsigned long long* virt_out;     /* TILE_EXPAND_VIRTUAL: where the entries go */
+  const unsigned long long* virt;   /* TILE_LEAF: when set, parent i of the launch is entry virt[i] applied to record (entry >> 32) of `in` */
 };
 
 /* K2's enumerate_split sink, DirectEmitter, lives in incremental.cuh (host-checkable). */
@@ -1112,7 +1118,7 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
   constexpr int PARENTS = CFG::PARENTS, POOL = CFG::POOL, GROUPS = CFG::GROUPS, GT = CFG::GROUP_THREADS;
   constexpr int SYNC = GROUPS == 1 ? 0 : GT; /* 0: plain __syncthreads */
   constexpr bool LEAF = MODE == TILE_LEAF;
-  constexpr bool ATOMIC = MODE == TILE_EXPAND_ATOMIC;
+  constexpr bool ATOMIC = MODE == TILE_EXPAND_ATOMIC || MODE == TILE_EXPAND_VIRTUAL;
   if (out.n_in) n = (size_t)*out.n_in; /* a frontier sized on the device: the grid was launched for an upper bound */
   if ((size_t)blockIdx.x * GROUPS * PARENTS >= n) return; /* no tile for this block (the same for all its threads) */
   extern __shared__ __align__(16) unsigned char smem[];
@@ -1153,8 +1159,17 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         const bool mine = valid && (u32)tid >= lo && (u32)tid < lo + len;
         u32 inert_nodes = 0, inert_moves = 0;
         if (mine) {
-          Pos p = load_pos(in.rec, in.stride, first + i);
-          if (meta_stm(p.meta) == 0) p = mirror(p);
+          Pos p;
+          if (out.virt) { /* the parent is made here: its record's side to move normalised to white, then the move */
+            const unsigned long long e = out.virt[first + i];
+            p = load_pos(in.rec, in.stride, (size_t)(e >> 32));
+            u16 mv = (u16)e;
+            if (meta_stm(p.meta) == 1) p = mirror(p), mv ^= 56 | (56 << 6);
+            make_move_kind<0, false>(p, tb, mv, (int)(e >> 16) & 7);
+          } else {
+            p = load_pos(in.rec, in.stride, first + i);
+            if (meta_stm(p.meta) == 0) p = mirror(p);
+          }
           const TContext ctx = t_context(p, tb);
           p.meta = (with_king_squares(p) & ~(0xFFFFULL << META_BASE)) | ((u64)ctx.base << META_BASE);
           put_tile_parent(sh, tid, p);
@@ -1171,7 +1186,9 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         }
         if (lo == 0 && tid < PARENTS && (tid & 15) == 0) { /* the next tile's parents towards L2, one request per 128-byte line */
           const size_t next_first = (size_t)sh.next_tile * PARENTS + tid;
-          if (next_first < n) {
+          if (next_first < n && out.virt) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(out.virt + first + next_first)); /* 16 entries are one 128-byte line */
+          } else if (next_first < n) {
 #pragma unroll
             for (int w = 0; w < POS_WORDS / 2; w++) { /* 16 records of a pair array are two 128-byte lines */
               asm volatile("prefetch.global.L2 [%0];" ::"l"(in.rec + ((size_t)w * in.stride + first + next_first) * 2));
@@ -1203,7 +1220,8 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         }
         if (MULTI_ROOT) {
           group_sync<SYNC>(group);
-          if (mine && sh.parent_nodes[tid]) atomicAdd(out.nodes + in.roots[first + i], (unsigned long long)sh.parent_nodes[tid]);
+          if (mine && sh.parent_nodes[tid])
+            atomicAdd(out.nodes + in.roots[out.virt ? (size_t)(out.virt[first + i] >> 32) : first + i], (unsigned long long)sh.parent_nodes[tid]);
         }
         group_sync<SYNC>(group); /* the pool and the cursor are free again */
         lo += len;
@@ -1269,6 +1287,11 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
             continue;
           }
           const int parent = PB_IN_BOUNDS((e >> 16) & 0xFFF, PARENTS) ? (e >> 16) & 0xFFF : 0;
+          if (MODE == TILE_EXPAND_VIRTUAL) { /* the child stays a (parent, move) pair */
+            if (PB_IN_BOUNDS(out_base + w + c, out.out_cap))
+              out.virt_out[out_base + w + c] = ((unsigned long long)(first + tile * PARENTS + parent) << 32) | ((unsigned long long)(e >> 28) << 16) | (e & 0xFFFF);
+            continue;
+          }
           Pos q = tile_parent(sh, parent);
           make_move_kind<-1, false, true>(q, tb, (u16)(e & 0xFFFF), (int)(e >> 28)); /* == make_move, without the piece lookup */
           const size_t o = (size_t)(out_base + w + c);

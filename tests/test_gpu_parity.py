@@ -644,3 +644,25 @@ def test_shard_assignment_is_the_documented_hash_of_the_record(pb, engine, playo
             owner = D.shard_of(p.pack64(), count)
             got = [engine.perft_shard(p, 2, 0, s, count) for s in range(count)]
             assert got == [whole if s == owner else 0 for s in range(count)], (i, count)
+
+
+def test_virtual_ply_and_materialised_ply_give_the_same_counts(pb, monkeypatch):
+    """With three plies left the ply above K2 is not materialised (K1 writes 8-byte (parent, move) entries, K2 makes its
+    parents itself); PABI_NO_VIRTUAL_PLY=1 keeps the round-1 behaviour.  Both must agree everywhere: white and black
+    grandparents (the mirrored make_move), castling / en passant / promotion positions, per-root batches, and a frontier so
+    small (4 096 records = 32 768 entries) that the virtual ply is cut into several chunks."""
+    cases = [(KIWIPETE, 3, 97862), (KIWIPETE, 4, 4085603), (KIWIPETE, 5, 193690690),
+             ("n1n5/PPPk4/8/8/8/8/4Kppp/5N1N b - - 0 1", 5, 3605103), ("n1n5/PPPk4/8/8/8/8/4Kppp/5N1N b - - 0 1", 6, 71179139),
+             ("8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - - 0 1", 6, 11030083),
+             ("r3k2r/Pppp1ppp/1b3nbN/nP6/BBP1P3/q4N2/Pp1P2PP/R2Q1RK1 w kq - 0 1", 5, 15833292)]
+    roots = [pb.Position.try_from(fen) for fen, _, _ in cases]
+    for env in ("0", "1"):
+        monkeypatch.setenv("PABI_NO_VIRTUAL_PLY", env)
+        e, tiny = pb.Engine(0), pb.Engine(0, frontier_capacity=4096)
+        for (fen, depth, nodes), root in zip(cases, roots):
+            assert e.perft(root, depth) == nodes, (env, fen, depth)
+            if nodes < 20_000_000:
+                assert tiny.perft(root, depth) == nodes, (env, "tiny", fen, depth)
+        assert e.perft_batch(roots, 3).tolist() == tiny.perft_batch(roots, 3).tolist() == [pb.Engine.perft(e, r, 3) for r in roots]
+        assert sum(e.perft_shard(roots[0], 5, 2, i, 3) for i in range(3)) == 193690690
+        e.close(), tiny.close()
