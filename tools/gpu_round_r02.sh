@@ -17,12 +17,12 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 echo "launch list rc=$?"
 SMALL="python bench.py --depth 7 --steps 1 --warmup 1 --no-cpu --no-extra"
 $SMALL > $OUT/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_tile -s 5 -c 1 -f -o $OUT/leaf_$TAG $SMALL > $OUT/ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:k_tile<\(pabi::TileMode\)0' -s 1 -c 1 -f -o $OUT/leaf_$TAG $SMALL > $OUT/ncu_full_$TAG.log 2>&1
 echo "full capture rc=$?"
 # instruction counts of every leaf launch of one perft(8) (second call of the process: warm)
 D8="python tools/quick_perft.py 8"
 $D8 > $OUT/plain3_$TAG.log 2>&1 &&
 ncu --metrics smsp__inst_executed.sum,smsp__thread_inst_executed.sum,gpu__time_duration.sum,sm__cycles_elapsed.max,smsp__cycles_active.avg,sm__inst_executed_pipe_alu.sum,sm__inst_executed_pipe_fma.sum,sm__inst_executed_pipe_xu.sum,sm__inst_executed_pipe_lsu.sum \
-  --clock-control none --kernel-name-base demangled -k 'regex:k_tile<\(pabi::TileMode\)0' -c 12 --csv --log-file $OUT/leaf_inst_$TAG.csv $D8 > $OUT/ncu_inst_$TAG.log 2>&1
+  --clock-control none --kernel-name-base demangled -k 'regex:k_tile<\(pabi::TileMode\)0' -c 2 --csv --log-file $OUT/leaf_inst_$TAG.csv $D8 > $OUT/ncu_inst_$TAG.log 2>&1
 echo "inst count rc=$?"
 ls -la $OUT | tail -12

@@ -2,7 +2,7 @@
 tools/gpu_round_r02.sh:
 
   gpurun_out/leaf_inst_<tag>.csv   ncu --metrics smsp__inst_executed.sum,... over the K2 launches of startpos perft(8)
-                                   (four launches per perft: the ply-6 frontier is walked in four chunks)
+                                   (one launch per perft since the ply above it is virtual; four while it was materialised)
   gpurun_out/leaf_<tag>.ncu-rep    ncu --set full capture of the depth-7 K2 launch (DRAM bytes, pipes, lanes)
 
     python tools/leaf_counts.py <tag>
@@ -17,7 +17,6 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 tag = sys.argv[1]
-LAUNCHES_PER_PERFT8 = 4
 PARENTS, CHILDREN = 119_060_324, 3_195_901_860   # plies 6 and 7 of the start position
 
 rows = list(csv.reader(open(ROOT / f"gpurun_out/leaf_inst_{tag}.csv")))
@@ -29,8 +28,9 @@ for r in rows[hi + 1:]:
         rec = dict(zip(header, r))
         per_launch[int(rec["ID"])][rec["Metric Name"]] = float(rec["Metric Value"].replace(",", ""))
 ids = sorted(per_launch)
-assert len(ids) >= 2 * LAUNCHES_PER_PERFT8, "expected the leaf launches of two perft(8) calls"
-step = [per_launch[i] for i in ids[LAUNCHES_PER_PERFT8:2 * LAUNCHES_PER_PERFT8]]  # the second (warm) perft(8)
+assert len(ids) >= 2 and len(ids) % 2 == 0, "expected the leaf launches of two perft(8) calls (tools/quick_perft.py 8)"
+LAUNCHES_PER_PERFT8 = len(ids) // 2   # 4 while ply 6 was materialised in chunks, 1 with the virtual ply
+step = [per_launch[i] for i in ids[LAUNCHES_PER_PERFT8:]]  # the second (warm) perft(8)
 tot = lambda k: sum(l[k] for l in step)
 
 raw = subprocess.run(["ncu", "-i", str(ROOT / f"gpurun_out/leaf_{tag}.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
