@@ -54,9 +54,14 @@ for i in range(len(sample)):
         C.memmove(buf.ctypes.data + 112 * k, sample.ctypes.data + 112 * i, 112)
         lib.oracle_make_move(C.cast(buf.ctypes.data + 112 * k, C.POINTER(oracle.Position)), int(m))
         k += 1
-buf["hash"] = 0
-assert buf.tobytes() == children.tobytes()
-print(f"children: {len(children)} positions equal field for field", flush=True)
+assert buf.tobytes() == children.tobytes()  # all 112 bytes, Position::hash included
+print(f"children: {len(children)} positions equal field for field (hash included)", flush=True)
+import brute  # the independent mailbox generator: move sets and in_check of a 600 000-position sample
+sample = np.ascontiguousarray(positions[::5][:600_000])
+soff, smv = e.generate_moves_batch(sample)
+bad, first, total = brute.compare_batch(sample, soff, smv, e.in_check_batch(sample))
+assert bad == 0 and total == len(smv), first
+print(f"brute-force generator: {total} moves of {len(sample)} positions agree as sets, in_check agrees", flush=True)
 ic = e.in_check_batch(positions[:500_000])
 ai = e.attack_info_batch(positions[:500_000])
 assert np.array_equal(ic, ai[:, 1] != 0)
