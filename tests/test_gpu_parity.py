@@ -666,3 +666,25 @@ def test_virtual_ply_and_materialised_ply_give_the_same_counts(pb, monkeypatch):
         assert e.perft_batch(roots, 3).tolist() == tiny.perft_batch(roots, 3).tolist() == [pb.Engine.perft(e, r, 3) for r in roots]
         assert sum(e.perft_shard(roots[0], 5, 2, i, 3) for i in range(3)) == 193690690
         e.close(), tiny.close()
+
+
+def test_move_lists_of_positions_with_more_moves_than_a_staging_column(pb, engine, vectors):
+    """The fused list kernel stages at most 64 moves per position; a warp that holds a fatter position regenerates its lists
+    through a sliding window.  Positions with up to 218 legal moves, alone, repeated, and mixed into ordinary batches of
+    ragged sizes, must still come out in the reference's order."""
+    fat = ["knq5/ppQ1qQQ1/2q4q/5Q2/1Q1Q3q/2qQ3q/Q4qPP/q1Q3NK w - - 0 1",           # ~120 moves
+           "R6R/3Q4/1Q4Q1/4Q3/2Q4Q/Q4Q2/pp1Q4/kBNN1KB1 w - - 0 1",                  # 218 moves, the record
+           "3Q4/1Q4Q1/4Q3/2Q4R/Q4Q2/3Q4/1Q4Rp/1K1BBNNk w - - 0 1",                  # 218 moves
+           "n1n5/PPPk4/8/8/8/8/4Kppp/5N1N b - - 0 1"]                              # promotions on both wings
+    fat_positions = [oracle.parse(f) for f in fat]
+    assert max(len(oracle.generate_moves(p)) for p in fat_positions) == 218
+    ordinary = [oracle.parse(c["fen"]) for c in vectors["move_lists"]]
+    for batch in (fat_positions, fat_positions * 40, ordinary + fat_positions, (ordinary * 3 + fat_positions[:2]) * 7, fat_positions[1:2] * 33):
+        arr = oracle.positions_array(batch)
+        offsets, moves = engine.generate_moves_batch(arr)
+        want_offsets, want_moves = oracle.generate_moves_batch(arr)
+        assert np.array_equal(offsets, want_offsets) and np.array_equal(moves, want_moves), len(batch)
+        # and with an output array that is too small: the required size comes back, nothing is written past the end
+        small = np.full(16, 0xFFFF, dtype=np.uint16)
+        offsets2, moves2 = engine.generate_moves_batch(arr, None, small)
+        assert np.array_equal(offsets2, want_offsets) and np.array_equal(moves2, want_moves) and (small == 0xFFFF).all()
