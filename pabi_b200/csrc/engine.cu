@@ -805,6 +805,14 @@ int perft_impl(pabi_cuda_ctx* ctx, const pabi_position_t* roots, size_t n, int d
       }
       if (acc == WEIGHTED) ctx->merged_away = 0;
     }
+#ifdef PABI_STATS
+    {
+      unsigned long long st[3];
+      CK(cudaMemcpy(st, ctx->d_visited + 2, sizeof st, cudaMemcpyDeviceToHost));
+      std::fprintf(stderr, "K2 stats: %llu pool passes, %llu overflowed passes, fullest pool %llu entries\n", st[0], st[1], st[2]);
+      CK(cudaMemset(ctx->d_visited + 2, 0, sizeof st));
+    }
+#endif
     for (int slot : ctx->fast_interior) ctx->interior += ctx->h_fast[slot];
     for (int slot : ctx->fast_leaf) ctx->leaf_parents += ctx->h_fast[slot];
     ctx->interior += ctx->h_result[2];
@@ -861,7 +869,8 @@ int pabi_cuda_create(int device, size_t frontier_capacity, pabi_cuda_ctx** out) 
     CK(cudaMallocHost(&ctx->h_bad_roots, sizeof(u32)));
     *ctx->h_bad_roots = 0;
     CK(cudaMalloc(&ctx->d_result, 4 * sizeof(u64)));
-    CK(cudaMalloc(&ctx->d_visited, 2 * sizeof(unsigned long long))); /* [0] statistics, [1] tile tickets */
+    CK(cudaMalloc(&ctx->d_visited, 8 * sizeof(unsigned long long))); /* [0] statistics, [1] tile tickets, [2..4] PABI_STATS builds */
+    CK(cudaMemset(ctx->d_visited, 0, 8 * sizeof(unsigned long long)));
     CK(cudaMallocHost(&ctx->h_result, 4 * sizeof(u64)));
     /* kernels that stage the table image need more than the default 48 KB of dynamic shared memory */
     CK(cudaFuncSetAttribute(k_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM));

@@ -1050,6 +1050,7 @@ struct TileGroupShared {
   u32 parent_nodes[CFG::PARENTS]; /* K2, multi-root: nodes below each parent */
   u64 warp_sums[CFG::GROUP_THREADS / 32 + 1];
   unsigned long long next_tile; /* TILE_LEAF: the group's next tile (ticket counter), taken while the current tile is in phase A */
+  u32 start_len, fullest, shrunk; /* TILE_LEAF: parents per pool pass of the next tile, and what decides it (thread 0 only) */
   u32 cursor;                   /* TILE_LEAF: pool entries reserved so far, other << 16 | clean (DirectEmitter) */
   u32 overflow;                 /* TILE_LEAF: a reservation did not fit: the range of parents is halved and redone */
 };
@@ -1135,7 +1136,12 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
   /* K2 takes tiles from a ticket counter (their cost varies, and a static split leaves a tail of idle
    * groups at the end of the launch); K1/K3 tiles are cheap and uniform enough for a static stride */
   if (LEAF) { /* the ticket of a tile is taken while the tile before it is in phase A, so that its parents can be prefetched */
-    if (tid == 0) sh.next_tile = atomicAdd(out.ticket, 1ULL);
+    /* start_len: how many parents of a tile share one pass through the pool.  The whole tile at first; a pass whose entries do
+     * not fit halves it, and the NEXT tiles start from the halved length instead of overflowing again (in positions with few
+     * inert moves four tiles in ten overflowed, each time throwing away the enumeration of all their parents); it doubles again
+     * after a tile whose fullest pass used at most 35 % of the pool.  Kept by thread 0 in shared memory: written before the
+     * first barrier of a tile, read by the others after it. */
+    if (tid == 0) sh.next_tile = atomicAdd(out.ticket, 1ULL), sh.start_len = PARENTS, sh.fullest = 0, sh.shrunk = 0;
     group_sync<SYNC>(group);
   }
   for (size_t tile = (size_t)blockIdx.x * GROUPS + group;; tile += (size_t)gridDim.x * GROUPS) {
@@ -1151,11 +1157,14 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
        * [lo, lo + len); a range whose entries do not fit the pool is halved and redone (a single parent always fits). */
       static_assert(POOL >= 1024 && POOL <= 32768, "one parent's moves fit; the packed cursor has 16 bits per class");
       const u32 tile_parents = (u32)min((size_t)PARENTS, n - tile * PARENTS);
-      u32 lo = 0, len = PARENTS;
+      u32 lo = 0, len = 0; /* len = 0: the first pass of the tile */
       while (lo < tile_parents) {
         if (tid == 0) sh.cursor = 0, sh.overflow = 0;
         group_sync<SYNC>(group);
-        if (tid == 0 && lo == 0 && len == (u32)PARENTS) sh.next_tile = atomicAdd(out.ticket, 1ULL); /* the next tile, once per tile */
+        if (len == 0) {
+          if (tid == 0) sh.next_tile = atomicAdd(out.ticket, 1ULL); /* the next tile, once per tile */
+          len = sh.start_len;
+        }
         const bool mine = valid && (u32)tid >= lo && (u32)tid < lo + len;
         u32 inert_nodes = 0, inert_moves = 0;
         if (mine) {
@@ -1180,7 +1189,11 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         }
         group_sync<SYNC>(group);
         if (sh.overflow) { /* the same for every thread of the group: read after the barrier, reset after the next one */
+#ifdef PABI_STATS
+          if (tid == 0) atomicAdd(out.visited + 3, 1ULL);
+#endif
           len = len > 1 ? len >> 1 : 1;
+          if (tid == 0) sh.shrunk = 1;
           group_sync<SYNC>(group);
           continue;
         }
@@ -1199,9 +1212,12 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         inert_children += inert_moves;
         if (MULTI_ROOT) { if (mine) sh.parent_nodes[tid] = inert_nodes; }
         else if (mine) acc += ACC == WEIGHTED ? (u64)inert_nodes * in.mult[first + i] : (u64)inert_nodes;
+#ifdef PABI_STATS
+        if (tid == 0) atomicAdd(out.visited + 2, 1ULL), atomicMax(out.visited + 4, (unsigned long long)((sh.cursor & 0xFFFF) + (sh.cursor >> 16)));
+#endif
         const u32 cursor = sh.cursor;
         const u32 clean_here = cursor & 0xFFFF, others = cursor >> 16, end = clean_here + others;
-        if (tid == 0 && end) atomicAdd(out.visited, (unsigned long long)end); /* statistics: positions at the last ply but one */
+        if (tid == 0 && end) atomicAdd(out.visited, (unsigned long long)end), sh.fullest = max(sh.fullest, end); /* statistics: positions at the last ply but one */
         if (MULTI_ROOT) group_sync<SYNC>(group); /* the per-parent counters are set */
         for (u32 c = tid; c < end; c += GT) {
           const u32 slot = c < clean_here ? c : POOL - others + (c - clean_here);
@@ -1225,6 +1241,11 @@ k_tile(DeviceTables dt, Frontier in, size_t first, size_t n, const u64* __restri
         }
         group_sync<SYNC>(group); /* the pool and the cursor are free again */
         lo += len;
+      }
+      if (tid == 0) { /* the next tile's starting length (thread 0 passes its first barrier only after this) */
+        if (sh.shrunk) sh.start_len = len;
+        else if (sh.start_len < (u32)PARENTS && sh.fullest * 20 <= (u32)POOL * 7) sh.start_len <<= 1;
+        sh.shrunk = 0, sh.fullest = 0;
       }
       continue;
     }
