@@ -7,7 +7,8 @@
 Workload (N = 1 .. 8): perft(8) from the standard start position, 84 998 978 956
 nodes (BASELINE.json configs[3]); one "step" is one complete perft(8).  With N > 1
 (torchrun, one process per GPU) the tree is cut at ply 4 (197 281 subtrees) and
-rank r walks the subtrees r, r+N, ...; the only collective is the final u64 sum.
+rank r walks the subtrees whose root record hashes to r (mod N); the only collective
+is the u64 sum at the end of every step.
 
 One JSON line on stdout (rank 0):
   value     nodes / device time (CUDA events on the launching stream, max over ranks)
@@ -451,7 +452,7 @@ def run_gpu(args) -> None:
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": device_ms_max / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": f"startpos perft({depth}), {NODES.get(depth, '?')} nodes, bit-exact count checked every step",
-                       "sharding": "single GPU" if world == 1 else f"root subtrees at ply {SPLIT_PLY}, rank r takes r, r+N, ...; one u64 all-reduce (NCCL) per step",
+                       "sharding": "single GPU" if world == 1 else f"root subtrees at ply {SPLIT_PLY}, cut by a hash of the subtree's root record (rank = hash mod N); one u64 all-reduce (NCCL) per step",
                        "l2": "frontier buffers (>= 7.6 GB at ply 6) are far larger than the 126 MB L2; no flush needed",
                        "frontier_capacity_records": args.capacity or 32 << 20},
             "e2e": {"value": nodes_total / (wall_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 112,

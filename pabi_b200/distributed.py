@@ -2,8 +2,8 @@
 
 perft subtrees are independent, so the path has no data exchange while it runs
 (SURVEY.md 8e): every rank expands the root breadth-first to `split_ply` on its
-own GPU (a few hundred microseconds of redundant work), walks the subtrees whose
-index is congruent to its rank, and the ranks then sum one 64-bit count with
+own GPU (about a hundred microseconds of redundant work), walks the subtrees whose
+root record hashes to its rank (`shard_of`), and the ranks then sum one 64-bit count with
 `torch.distributed.all_reduce` (NCCL over NVLink on GPUs, gloo in the CPU tests).
 """
 from __future__ import annotations
